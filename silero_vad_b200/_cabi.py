@@ -1,0 +1,124 @@
+"""ctypes binding of include/silero_vad_b200.h (the C ABI of libsilero_vad_b200.so).
+
+Fails loudly when the CUDA library is missing or cannot be loaded: there is no CPU fallback.
+"""
+import ctypes
+from pathlib import Path
+
+from .build import LIB, build
+
+_f32p = ctypes.c_void_p  # device or host float* passed as an integer address
+_lib = None
+
+EXPORTS = ["svad_abi_version", "svad_last_error", "svad_engine_create", "svad_engine_destroy",
+           "svad_engine_set_tile_rows", "svad_engine_sm_count", "svad_engine_launch_count",
+           "svad_forward_device", "svad_step_device", "svad_forward_host", "svad_step_host",
+           "svad_segment_params_default", "svad_speech_segments"]
+
+
+class SvadError(RuntimeError):
+    pass
+
+
+class SegmentParams(ctypes.Structure):
+    """struct svad_segment_params (include/silero_vad_b200.h)."""
+    _fields_ = [("sampling_rate", ctypes.c_int32), ("use_max_poss_sil_at_max_speech", ctypes.c_int32),
+                ("threshold", ctypes.c_double), ("neg_threshold", ctypes.c_double),
+                ("min_speech_duration_ms", ctypes.c_double), ("max_speech_duration_s", ctypes.c_double),
+                ("min_silence_duration_ms", ctypes.c_double), ("speech_pad_ms", ctypes.c_double),
+                ("min_silence_at_max_speech_ms", ctypes.c_double)]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(LIB)
+    if not path.exists():
+        path = build()
+    L = ctypes.CDLL(str(path))
+    i64, i32, vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
+    L.svad_abi_version.restype = i32
+    L.svad_last_error.restype = ctypes.c_char_p
+    L.svad_engine_create.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(vp)]
+    L.svad_engine_destroy.argtypes = [vp]
+    L.svad_engine_destroy.restype = None
+    L.svad_engine_set_tile_rows.argtypes = [vp, i32]
+    L.svad_engine_sm_count.argtypes = [vp]
+    L.svad_engine_launch_count.argtypes = [vp]
+    L.svad_engine_launch_count.restype = i64
+    L.svad_forward_device.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.svad_step_device.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.svad_forward_host.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64]
+    L.svad_step_host.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.svad_segment_params_default.argtypes = [ctypes.POINTER(SegmentParams)]
+    L.svad_segment_params_default.restype = None
+    L.svad_speech_segments.argtypes = [vp, i64, i64, i64, vp, ctypes.POINTER(SegmentParams), vp, vp, i64, ctypes.POINTER(i64)]
+    for name in EXPORTS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().svad_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(msg)
+        raise SvadError("silero_vad_b200 error %d: %s" % (rc, msg))
+
+
+class Engine:
+    """Owns one svad_engine (weights resident on one CUDA device)."""
+
+    def __init__(self, weights_path, device=0):
+        self._h = ctypes.c_void_p()
+        check(lib().svad_engine_create(str(weights_path).encode(), int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().svad_engine_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    @property
+    def sm_count(self):
+        return lib().svad_engine_sm_count(self._h)
+
+    @property
+    def launch_count(self):
+        return lib().svad_engine_launch_count(self._h)
+
+    def set_tile_rows(self, rows):
+        check(lib().svad_engine_set_tile_rows(self._h, rows))
+
+    def forward_device(self, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream=0):
+        check(lib().svad_forward_device(self._h, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream))
+
+    def step_device(self, sr, B, x1, state_in, prob, state_out, stream=0):
+        check(lib().svad_step_device(self._h, sr, B, x1, state_in, prob, state_out, stream))
+
+    def forward_host(self, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp):
+        check(lib().svad_forward_host(self._h, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp))
+
+    def step_host(self, sr, B, x1, state_in, prob, state_out):
+        check(lib().svad_step_host(self._h, sr, B, x1, state_in, prob, state_out))
+
+
+def speech_segments(probs, audio_lens, params):
+    """probs: C-contiguous float32 numpy [B, T]; audio_lens: int64 numpy [B].  Returns a list (per stream) of
+    (start, end) integer pairs in samples at the model rate."""
+    import numpy as np
+    probs = np.ascontiguousarray(probs, np.float32)
+    lens = np.ascontiguousarray(audio_lens, np.int64)
+    B, T = probs.shape
+    offs = np.zeros(B + 1, np.int64)
+    cap = B * (T // 2 + 2) + 1
+    bounds = np.zeros((cap, 2), np.int64)
+    n = ctypes.c_int64(0)
+    check(lib().svad_speech_segments(probs.ctypes.data, B, T, T, lens.ctypes.data, ctypes.byref(params), offs.ctypes.data,
+                                     bounds.ctypes.data, cap, ctypes.byref(n)))
+    assert n.value <= cap
+    return [[(int(a), int(b)) for a, b in bounds[offs[i]:offs[i + 1]]] for i in range(B)]

@@ -1,0 +1,345 @@
+// svad_api.cu -- CUDA kernel instantiations and the C ABI (include/silero_vad_b200.h) of the
+// B200-native Silero-VAD engine.  Build: nvcc -gencode arch=compute_100a,code=sm_100a (see build.py).
+//
+// Kernel `svad_fused_fp32<SR16, RM>`: one persistent CTA (256 threads, ~214 KB dynamic shared memory,
+// one CTA per SM) per tile of 4*RM streams; the whole per-chunk forward pass (STFT -> 4 conv -> LSTM ->
+// head) for all T chunks runs inside the launch with (h, c) and the audio context resident on the SM.
+// The weights are a linear "tape" in global memory (L2-resident, 0.89 MB) that thread 0 streams into a
+// two-stage shared-memory ring with cp.async.bulk (TMA bulk copy, completion on an mbarrier) one slab
+// ahead of the FFMA loops.  HBM traffic is the audio read once plus 4 B per chunk of probabilities.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+#include <string>
+
+#include "../../include/silero_vad_b200.h"
+#include "svad_tile.h"
+
+using namespace svad;
+
+// ------------------------------------------------------------------------------------------ device
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool SR16>
+struct GpuEnv {
+    float* sm;
+    uint64_t* full;  // [kStages] mbarriers
+    const float* tape;
+    int tid_;
+    __device__ __forceinline__ int tid() const { return tid_; }
+    __device__ __forceinline__ float* smem() { return sm; }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void issue(long it) {  // one thread
+        const int idx = (int)(it % Geo<SR16>::nslab), stage = (int)(it % kStages);
+        const uint32_t bytes = (uint32_t)Tape<SR16>::slab_len(idx) * 4u;
+        const uint32_t bar = smem_u32(full + stage);
+        const uint32_t dst = smem_u32(sm + SmemMap::stage + stage * SmemMap::stage_floats);
+        const float* src = tape + Tape<SR16>::slab_off(idx);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+    __device__ __forceinline__ const float* slab_acquire(long it) {
+        const int stage = (int)(it % kStages);
+        const uint32_t parity = (uint32_t)((it / kStages) & 1);
+        const uint32_t bar = smem_u32(full + stage);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+        return sm + SmemMap::stage + stage * SmemMap::stage_floats;
+    }
+    __device__ __forceinline__ void slab_release(long it, long total) {
+        if (tid_ == 0 && it + kStages < total) issue(it + kStages);
+    }
+};
+
+constexpr size_t kSmemBytes = (size_t)SmemMap::total_floats * 4 + 64;
+
+template <bool SR16, int RM>
+__global__ void __launch_bounds__(kThreads, 1) svad_fused_fp32(TileArgs a, int ntiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SmemMap::total_floats * 4);
+    GpuEnv<SR16> env{sm, full, a.tape, (int)threadIdx.x};
+    int my_tiles = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(full + s)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const long total = (long)my_tiles * a.T * Geo<SR16>::nslab;
+        for (long i = 0; i < kStages && i < total; i++) env.issue(i);
+    }
+    __syncthreads();
+    run_cta<SR16, RM>(env, a, (int)blockIdx.x, (int)gridDim.x, ntiles);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                               \
+    do {                                                                                          \
+        cudaError_t err__ = (x);                                                                  \
+        if (err__ != cudaSuccess) return fail(SVAD_ECUDA, "%s: %s", #x, cudaGetErrorString(err__)); \
+    } while (0)
+
+struct svad_engine {
+    int device = 0, sms = 0, tile_rows = 0;
+    float* d_tape[2] = {nullptr, nullptr};    // 0: 16 kHz, 1: 8 kHz
+    float* d_consts[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    // staging for the host-buffer entry points
+    float *h_pin = nullptr, *d_buf = nullptr;
+    size_t pin_floats = 0, dbuf_floats = 0;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" int svad_abi_version(void) { return 1; }
+extern "C" const char* svad_last_error(void) { return g_err.c_str(); }
+
+extern "C" int svad_engine_create(const char* weights_path, int device, svad_engine** out) {
+    if (!weights_path || !out) return fail(SVAD_EINVAL, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SVAD_ECUDA, "no CUDA device: silero_vad_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SVAD_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    TensorMap tm;
+    std::string err;
+    if (!read_container(weights_path, tm, err)) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
+    PackedBranch pb[2];
+    if (!pack_branch<true>(tm, pb[0], err) || !pack_branch<false>(tm, pb[1], err)) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if ((size_t)prop.sharedMemPerBlockOptin < kSmemBytes)
+        return fail(SVAD_ECUDA, "device offers %zu B shared memory per block, kernel needs %zu", (size_t)prop.sharedMemPerBlockOptin, kSmemBytes);
+    svad_engine* e = new (std::nothrow) svad_engine();
+    if (!e) return fail(SVAD_ENOMEM, "out of memory");
+    e->device = device;
+    e->sms = prop.multiProcessorCount;
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMalloc(&e->d_tape[b], pb[b].tape.size() * 4));
+        CUDA_TRY(cudaMalloc(&e->d_consts[b], pb[b].consts.size() * 4));
+        CUDA_TRY(cudaMemcpy(e->d_tape[b], pb[b].tape.data(), pb[b].tape.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(e->d_consts[b], pb[b].consts.data(), pb[b].consts.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    *out = e;
+    return SVAD_OK;
+}
+
+extern "C" void svad_engine_destroy(svad_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (int b = 0; b < 2; b++) { cudaFree(e->d_tape[b]); cudaFree(e->d_consts[b]); }
+    if (e->h_pin) cudaFreeHost(e->h_pin);
+    if (e->d_buf) cudaFree(e->d_buf);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int svad_engine_set_tile_rows(svad_engine* e, int rows) {
+    if (!e || !(rows == 0 || (rows >= 4 && rows <= 8))) return fail(SVAD_EINVAL, "tile rows must be 0 or 4..8");
+    e->tile_rows = rows;
+    return SVAD_OK;
+}
+extern "C" int svad_engine_sm_count(const svad_engine* e) { return e ? e->sms : 0; }
+extern "C" int64_t svad_engine_launch_count(const svad_engine* e) { return e ? e->launches : 0; }
+
+template <bool SR16, int RM>
+static int launch(svad_engine* e, const TileArgs& a, cudaStream_t st) {
+    auto kern = svad_fused_fp32<SR16, RM>;
+    static bool configured[16] = {};  // per device
+    if (!configured[e->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        configured[e->device & 15] = true;
+    }
+    const int ntiles = (a.B + 4 * RM - 1) / (4 * RM);
+    const int grid = ntiles < e->sms ? ntiles : e->sms;
+    kern<<<grid, kThreads, kSmemBytes, st>>>(a, ntiles);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return SVAD_OK;
+}
+
+// rows per thread that minimises (waves x rows): the FFMA work of a CTA step is proportional to RM.
+static int pick_rows(const svad_engine* e, int B) {
+    if (e->tile_rows) return e->tile_rows;
+    int best = 8;
+    long best_cost = -1;
+    for (int rm = 8; rm >= 4; rm--) {
+        const long tiles = (B + 4 * rm - 1) / (4 * rm);
+        const long waves = (tiles + e->sms - 1) / e->sms;
+        const long cost = waves * rm;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rm; }
+    }
+    return best;
+}
+
+template <bool SR16>
+static int launch_rm(svad_engine* e, const TileArgs& a, cudaStream_t st) {
+    switch (pick_rows(e, a.B)) {
+        case 4: return launch<SR16, 4>(e, a, st);
+        case 5: return launch<SR16, 5>(e, a, st);
+        case 6: return launch<SR16, 6>(e, a, st);
+        case 7: return launch<SR16, 7>(e, a, st);
+        default: return launch<SR16, 8>(e, a, st);
+    }
+}
+
+static int forward_impl(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const float* d_audio, const float* d_state_in,
+                        const float* d_ctx_in, int64_t ctx_ld, float* d_state_out, float* d_ctx_out, float* d_probs,
+                        int64_t ldp, cudaStream_t st) {
+    if (!e) return fail(SVAD_EINVAL, "null engine");
+    if (sr != 16000 && sr != 8000) return fail(SVAD_EINVAL, "Supported sampling rates: [8000, 16000] (got %d)", sr);
+    if (B < 0 || L < 0) return fail(SVAD_EINVAL, "negative size");
+    const int n = sr == 16000 ? 512 : 256;
+    const int64_t T = (L + n - 1) / n;
+    if (B == 0 || (T == 0 && !d_state_out && !d_ctx_out)) return SVAD_OK;
+    if ((T > 0 && (!d_audio || !d_probs)) || ld < L || ldp < T) return fail(SVAD_EINVAL, "bad audio/probs pointer or stride");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int br = sr == 16000 ? 0 : 1;
+    TileArgs a{};
+    a.audio = d_audio; a.ld = ld; a.L = L; a.B = B; a.T = T;
+    a.state_in = d_state_in; a.ctx_in = d_ctx_in; a.ctx_ld = ctx_ld;
+    a.state_out = d_state_out; a.ctx_out = d_ctx_out;
+    a.probs = d_probs; a.ldp = ldp; a.tape = e->d_tape[br]; a.consts = e->d_consts[br];
+    return sr == 16000 ? launch_rm<true>(e, a, st) : launch_rm<false>(e, a, st);
+}
+
+extern "C" int svad_forward_device(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const float* d_audio,
+                                   const float* d_state_in, const float* d_ctx_in, float* d_state_out, float* d_ctx_out,
+                                   float* d_probs, int64_t ldp, void* stream) {
+    return forward_impl(e, sr, B, L, ld, d_audio, d_state_in, d_ctx_in, sr == 16000 ? 64 : 32, d_state_out, d_ctx_out, d_probs,
+                        ldp, (cudaStream_t)stream);
+}
+
+extern "C" int svad_step_device(svad_engine* e, int sr, int B, const float* d_input, const float* d_state_in, float* d_prob,
+                                float* d_state_out, void* stream) {
+    if (sr != 16000 && sr != 8000) return fail(SVAD_EINVAL, "Supported sampling rates: [8000, 16000] (got %d)", sr);
+    const int n = sr == 16000 ? 512 : 256, ctx = n / 8;
+    if (B > 0 && (!d_input || !d_prob)) return fail(SVAD_EINVAL, "null input/prob");
+    // input rows are [context | chunk]: the chunk is the "audio", the context the carried-in samples
+    return forward_impl(e, sr, B, n, ctx + n, d_input + ctx, d_state_in, d_input, ctx + n, d_state_out, nullptr, d_prob, 1,
+                        (cudaStream_t)stream);
+}
+
+// ---- host-buffer twins -------------------------------------------------------------------------
+// Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are DMA'd directly;
+// pageable ones are staged through the engine's pinned buffer first.
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+static int ensure_staging(svad_engine* e, size_t floats) {
+    if (floats > e->pin_floats) {
+        if (e->h_pin) cudaFreeHost(e->h_pin);
+        e->h_pin = nullptr; e->pin_floats = 0;
+        CUDA_TRY(cudaMallocHost(&e->h_pin, floats * 4));
+        e->pin_floats = floats;
+    }
+    if (floats > e->dbuf_floats) {
+        if (e->d_buf) cudaFree(e->d_buf);
+        e->d_buf = nullptr; e->dbuf_floats = 0;
+        CUDA_TRY(cudaMalloc(&e->d_buf, floats * 4));
+        e->dbuf_floats = floats;
+    }
+    return SVAD_OK;
+}
+
+extern "C" int svad_forward_host(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const float* audio, const float* state_in,
+                                 const float* ctx_in, float* state_out, float* ctx_out, float* probs, int64_t ldp) {
+    if (!e) return fail(SVAD_EINVAL, "null engine");
+    if (sr != 16000 && sr != 8000) return fail(SVAD_EINVAL, "Supported sampling rates: [8000, 16000] (got %d)", sr);
+    if (B < 0 || L < 0 || ld < L) return fail(SVAD_EINVAL, "bad size");
+    if (B == 0) return SVAD_OK;
+    const int n = sr == 16000 ? 512 : 256, ctx = n / 8;
+    const int64_t T = (L + n - 1) / n;
+    if (T > 0 && (!audio || !probs || ldp < T)) return fail(SVAD_EINVAL, "bad audio/probs");
+    CUDA_TRY(cudaSetDevice(e->device));
+    // device layout: audio [B][L] | state [2][B][128] | ctx [B][ctx] | probs [B][T]   (each 16-float aligned)
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_audio = 0, o_state = al((size_t)B * L), o_ctx = o_state + al((size_t)2 * B * 128),
+                 o_probs = o_ctx + al((size_t)B * ctx), total = o_probs + al((size_t)B * T);
+    int rc = ensure_staging(e, total);
+    if (rc) return rc;
+    float *hp = e->h_pin, *dp = e->d_buf;
+    const bool audio_direct = T > 0 && ld == L && is_pinned(audio);
+    const bool probs_direct = T > 0 && ldp == T && is_pinned(probs);
+    if (!audio_direct && T > 0)
+        for (int b = 0; b < B; b++) memcpy(hp + o_audio + (size_t)b * L, audio + (size_t)b * ld, (size_t)L * 4);
+    if (state_in) memcpy(hp + o_state, state_in, (size_t)2 * B * 128 * 4);
+    if (ctx_in) memcpy(hp + o_ctx, ctx_in, (size_t)B * ctx * 4);
+    cudaStream_t st = e->stream;
+    if (T > 0)
+        CUDA_TRY(cudaMemcpyAsync(dp + o_audio, audio_direct ? audio : hp + o_audio, (size_t)B * L * 4, cudaMemcpyHostToDevice, st));
+    if (state_in) CUDA_TRY(cudaMemcpyAsync(dp + o_state, hp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyHostToDevice, st));
+    if (ctx_in) CUDA_TRY(cudaMemcpyAsync(dp + o_ctx, hp + o_ctx, (size_t)B * ctx * 4, cudaMemcpyHostToDevice, st));
+    rc = forward_impl(e, sr, B, L, L, dp + o_audio, state_in ? dp + o_state : nullptr, ctx_in ? dp + o_ctx : nullptr, ctx,
+                      state_out ? dp + o_state : nullptr, ctx_out ? dp + o_ctx : nullptr, dp + o_probs, T, st);
+    if (rc) return rc;
+    if (T > 0) CUDA_TRY(cudaMemcpyAsync(probs_direct ? probs : hp + o_probs, dp + o_probs, (size_t)B * T * 4, cudaMemcpyDeviceToHost, st));
+    if (state_out) CUDA_TRY(cudaMemcpyAsync(hp + o_state, dp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyDeviceToHost, st));
+    if (ctx_out) CUDA_TRY(cudaMemcpyAsync(hp + o_ctx, dp + o_ctx, (size_t)B * ctx * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int b = 0; b < B && T > 0 && !probs_direct; b++) memcpy(probs + (size_t)b * ldp, hp + o_probs + (size_t)b * T, (size_t)T * 4);
+    if (state_out) memcpy(state_out, hp + o_state, (size_t)2 * B * 128 * 4);
+    if (ctx_out) memcpy(ctx_out, hp + o_ctx, (size_t)B * ctx * 4);
+    return SVAD_OK;
+}
+
+extern "C" int svad_step_host(svad_engine* e, int sr, int B, const float* input, const float* state_in, float* prob,
+                              float* state_out) {
+    if (!e) return fail(SVAD_EINVAL, "null engine");
+    if (sr != 16000 && sr != 8000) return fail(SVAD_EINVAL, "Supported sampling rates: [8000, 16000] (got %d)", sr);
+    if (B < 0) return fail(SVAD_EINVAL, "bad size");
+    if (B == 0) return SVAD_OK;
+    if (!input || !prob) return fail(SVAD_EINVAL, "null input/prob");
+    const int n = sr == 16000 ? 512 : 256, ctx = n / 8, W = ctx + n;
+    CUDA_TRY(cudaSetDevice(e->device));
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_in = 0, o_state = al((size_t)B * W), o_prob = o_state + al((size_t)2 * B * 128), total = o_prob + al((size_t)B);
+    int rc = ensure_staging(e, total);
+    if (rc) return rc;
+    float *hp = e->h_pin, *dp = e->d_buf;
+    memcpy(hp + o_in, input, (size_t)B * W * 4);
+    if (state_in) memcpy(hp + o_state, state_in, (size_t)2 * B * 128 * 4);
+    cudaStream_t st = e->stream;
+    CUDA_TRY(cudaMemcpyAsync(dp + o_in, hp + o_in, (size_t)B * W * 4, cudaMemcpyHostToDevice, st));
+    if (state_in) CUDA_TRY(cudaMemcpyAsync(dp + o_state, hp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyHostToDevice, st));
+    rc = svad_step_device(e, sr, B, dp + o_in, state_in ? dp + o_state : nullptr, dp + o_prob, state_out ? dp + o_state : nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hp + o_prob, dp + o_prob, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (state_out) CUDA_TRY(cudaMemcpyAsync(hp + o_state, dp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(prob, hp + o_prob, (size_t)B * 4);
+    if (state_out) memcpy(state_out, hp + o_state, (size_t)2 * B * 128 * 4);
+    return SVAD_OK;
+}

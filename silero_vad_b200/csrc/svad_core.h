@@ -1,0 +1,495 @@
+// svad_core.h -- per-thread arithmetic of the fused fp32 Silero-VAD kernel (sm_100a).
+//
+// One CTA (256 threads) owns a tile of up to 32 stream "slots" and walks them through time.
+// Everything a thread does between two CTA barriers is a function in this header, written so
+// that the same source compiles (a) as __device__ code for the CUDA kernel in
+// svad_kernel_fp32.cu and (b) as plain C++ for the barrier-phase emulator tests/emu/ uses to
+// check layouts and index algebra on a machine without a GPU.  No warp shuffles in here for
+// that reason; cross-thread traffic goes through shared memory only.
+//
+// What is computed (reference: silero_vad.jit::_model / _model_8k):
+//   STFT   4 Hann-windowed N-point real DFTs per chunk (N = 256 @16k / 128 @8k), hop N/2, over
+//          [context | chunk | reflect-pad]; done as a two-pass FFT (N = 16*NQ): pass A = NQ-point
+//          DFTs over q for each residue r (two real sequences per complex FFT), twiddle, pass C =
+//          16-point DFTs over r.  Equivalent to the reference's conv with forward_basis_buffer
+//          (silero_vad.jit::_model.stft.transform_).
+//   enc0-3 Conv1d k=3 pad=1 strides 1,2,2,1 + ReLU with the zero-padding taps skipped.
+//   LSTM   gates = [x ; h] . [W_ih ; W_hh]^T + b, order i,f,g,o (torch.lstm_cell).
+//   head   sigmoid(w . relu(h') + b).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SVAD_HD __host__ __device__ __forceinline__
+#else
+#define SVAD_HD inline
+#endif
+
+namespace svad {
+
+constexpr int kThreads = 256;
+constexpr int kSlots = 32;   // stream slots per CTA tile (row dimension of every GEMM)
+constexpr int kHid = 128;
+constexpr int kGates = 512;
+constexpr int kStageBytes = 32768;  // one weight-tape slab buffer
+constexpr int kStages = 2;
+
+struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(8) f2 { float x, y; };
+
+// ---------------------------------------------------------------- branch geometry
+template <bool SR16>
+struct Geo {
+    static constexpr int n = SR16 ? 512 : 256;     // chunk samples
+    static constexpr int ctx = SR16 ? 64 : 32;     // context_size_samples
+    static constexpr int N = SR16 ? 256 : 128;     // filter_length
+    static constexpr int hop = N / 2;              // hop_length
+    static constexpr int F = N / 2 + 1;            // bins: 129 / 65
+    static constexpr int NQ = N / 16;              // pass-A DFT length: 16 / 8
+    static constexpr int L1 = ctx + n;             // 576 / 288
+    // enc0 slabs: channels per slab (each channel = 3 taps x 128 floats = 1536 B)
+    static constexpr int e0_nslab = SR16 ? 7 : 4;
+    static constexpr int e0_cps = SR16 ? 19 : 17;  // max channels per slab (<= 21)
+    static constexpr int nslab = e0_nslab + 4 + 1 + 1 + 16;
+};
+
+// ---------------------------------------------------------------- shared-memory map (float offsets)
+// mag  [4][F][32]      (later aliased by e1 [2][64][32], e2 [64][32], e3 [128][32])
+// e0   [4][128][32]    (aliased by the FFT exchange planes Zre/Zim [32][257] during the STFT)
+// h    [128][32]
+// consts: b0[128] b1[64] b2[64] b3[128] bl[512] wout[128] bout[1] pad[3] win[256]
+struct SmemMap {
+    static constexpr int mag = 0;
+    static constexpr int mag_floats = 4 * 129 * kSlots;          // 16512
+    static constexpr int e1 = mag;                               // [2][64][32]
+    static constexpr int e2 = e1 + 2 * 64 * kSlots;              // [64][32]
+    static constexpr int e3 = e2 + 64 * kSlots;                  // [128][32]
+    static constexpr int e0 = mag + mag_floats;
+    static constexpr int zpitch = 257;
+    static constexpr int e0_floats = 2 * kSlots * zpitch;        // 16448 >= 4*128*32
+    static constexpr int zre = e0;
+    static constexpr int zim = e0 + kSlots * zpitch;
+    static constexpr int h = e0 + e0_floats;
+    static constexpr int consts = h + kHid * kSlots;
+    static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_bout = 1024, c_win = 1028;
+    static constexpr int consts_floats = 1028 + 256;
+    static constexpr int headp = consts + consts_floats;         // [32] probabilities of this step
+    static constexpr int stage = headp + kSlots;                 // must be 16B aligned (x4 bytes)
+    static constexpr int stage_floats = kStageBytes / 4;
+    static constexpr int total_floats = stage + kStages * stage_floats;
+};
+static_assert(SmemMap::e0_floats >= 4 * 128 * kSlots, "e0 region too small");
+static_assert(SmemMap::e3 + 128 * kSlots <= SmemMap::mag + SmemMap::mag_floats, "e1/e2/e3 alias overflow");
+static_assert(SmemMap::stage % 4 == 0, "stage alignment");
+
+// ---------------------------------------------------------------- thread coordinates
+struct Tc {
+    int tid, warp, lane, lm, ln;
+    SVAD_HD explicit Tc(int t) : tid(t), warp(t >> 5), lane(t & 31), lm((t >> 3) & 3), ln(t & 7) {}
+    // the 8 row slots of this thread are two float4 groups: [4*lm, 4*lm+4) and [16+4*lm, 16+4*lm+4)
+    SVAD_HD int row0() const { return 4 * lm; }
+    SVAD_HD int row1() const { return 16 + 4 * lm; }
+};
+
+// Slot validity for tiles of 4*RM streams (RM in [4,8]): every thread owns rows {4lm..4lm+3} and the first
+// RM-4 of {16+4lm..16+4lm+3}.  Streams are numbered over the valid slots in increasing slot order.
+template <int RM>
+SVAD_HD bool slot_valid(int s) { return s < 16 || (s & 3) < RM - 4; }
+template <int RM>
+SVAD_HD int slot_to_local(int s) {  // local stream index of a valid slot
+    return s < 16 ? s : 16 + (RM - 4) * ((s - 16) >> 2) + (s & 3);
+}
+
+// ---------------------------------------------------------------- persistent per-thread registers
+struct Regs {
+    float acc[64];   // GEMM accumulators of the current layer
+    float c[16];     // LSTM cell state: [row i][unit u] -> c[i*2+u]
+    float twr[16];   // pass-A twiddles W_N^{k1*r}, k1 < NQ
+    float twi[16];
+};
+
+// ---------------------------------------------------------------- small complex FFTs
+// X[k] = sum_n x[n] exp(-2 pi i k n / NP), in place, compile-time indices only.
+template <int K, int NP>
+SVAD_HD void tw_mul(float& re, float& im) {  // (re,im) *= exp(-2 pi i K / NP)
+    constexpr int k = ((K % NP) + NP) % NP;
+    if constexpr (k == 0) {
+    } else if constexpr (4 * k == NP) {          // -i
+        float t = re; re = im; im = -t;
+    } else if constexpr (2 * k == NP) {          // -1
+        re = -re; im = -im;
+    } else if constexpr (4 * k == 3 * NP) {      // +i
+        float t = re; re = -im; im = t;
+    } else if constexpr (8 * k == NP) {          // (1 - i)/sqrt2
+        constexpr float s = 0.70710678118654752440f;
+        float a = (re + im) * s, b = (im - re) * s; re = a; im = b;
+    } else if constexpr (8 * k == 3 * NP) {      // (-1 - i)/sqrt2
+        constexpr float s = 0.70710678118654752440f;
+        float a = (im - re) * s, b = -(re + im) * s; re = a; im = b;
+    } else if constexpr (8 * k == 5 * NP) {      // (-1 + i)/sqrt2
+        constexpr float s = 0.70710678118654752440f;
+        float a = -(re + im) * s, b = (re - im) * s; re = a; im = b;
+    } else if constexpr (8 * k == 7 * NP) {      // (1 + i)/sqrt2
+        constexpr float s = 0.70710678118654752440f;
+        float a = (re - im) * s, b = (re + im) * s; re = a; im = b;
+    } else {
+        // general: only k/NP in {1,3,5,7,...}/16 reach here (NP == 16)
+        constexpr double ang = -2.0 * 3.14159265358979323846 * (double)k / (double)NP;
+        // constexpr cos/sin are not available in C++17; table for sixteenths
+        constexpr float c16[16] = {1.0f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f,
+                                   0.0f, -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f,
+                                   -1.0f, -0.92387953251128675613f, -0.70710678118654752440f, -0.38268343236508977173f,
+                                   0.0f, 0.38268343236508977173f, 0.70710678118654752440f, 0.92387953251128675613f};
+        static_assert(NP == 16, "general twiddle only for 16ths");
+        (void)ang;
+        constexpr float wr = c16[k];                 // cos(2 pi k/16)
+        constexpr float wi = -c16[(k + 12) % 16];    // -sin(2 pi k/16) ; sin(x) = cos(x - pi/2) = c16[k-4]
+        float a = re * wr - im * wi, b = re * wi + im * wr; re = a; im = b;
+    }
+}
+
+// radix-2 decimation-in-frequency, natural order in, bit-reversed order out (bin k at index bitrev(k)).
+template <int NP, int LEN, int START>
+struct Dif {
+    SVAD_HD static void run(float (&re)[NP], float (&im)[NP]) {
+        if constexpr (LEN >= 2) {
+            constexpr int H = LEN / 2;
+            Bfly<0>(re, im);
+            Dif<NP, H, START>::run(re, im);
+            Dif<NP, H, START + H>::run(re, im);
+        }
+    }
+    template <int I>
+    SVAD_HD static void Bfly(float (&re)[NP], float (&im)[NP]) {
+        constexpr int H = LEN / 2;
+        if constexpr (I < H) {
+            float ar = re[START + I], ai = im[START + I], br = re[START + I + H], bi = im[START + I + H];
+            re[START + I] = ar + br; im[START + I] = ai + bi;
+            float dr = ar - br, di = ai - bi;
+            tw_mul<I*(NP / LEN), NP>(dr, di);
+            re[START + I + H] = dr; im[START + I + H] = di;
+            Bfly<I + 1>(re, im);
+        }
+    }
+};
+SVAD_HD constexpr int bitrev(int x, int bits) { int r = 0; for (int i = 0; i < bits; i++) if (x & (1 << i)) r |= 1 << (bits - 1 - i); return r; }
+SVAD_HD constexpr int ilog2(int x) { int r = 0; while ((1 << r) < x) r++; return r; }
+// after fft_dif, bin k sits at index bitrev(k)
+template <int NP>
+SVAD_HD void fft_dif(float (&re)[NP], float (&im)[NP]) { Dif<NP, NP, 0>::run(re, im); }
+template <int NP>
+constexpr int binpos(int k) { return bitrev(k, ilog2(NP)); }
+
+// ---------------------------------------------------------------- audio window fetch
+// Sample `i` (0 <= i < L1 + N/4) of the padded window [context | chunk | reflect] of chunk t:
+//   utils_vad.py:78 (context concat), silero_vad.jit::_model.stft.padding (reflect right by N/4),
+//   utils_vad.py:100-102 (zero tail).  `ctx_in` (may be null) supplies samples before time 0.
+template <bool SR16>
+SVAD_HD float window_sample(const float* audio, long L, const float* ctx_in, long t, int i) {
+    using G = Geo<SR16>;
+    if (i >= G::L1) i = 2 * G::L1 - 2 - i;           // xp[L1 + j] = x1[L1 - 2 - j]
+    long a = t * G::n - G::ctx + i;
+    if (a < 0) return ctx_in ? ctx_in[G::ctx + a] : 0.0f;
+    if (a >= L) return 0.0f;
+#if defined(__CUDA_ARCH__)
+    return __ldg(audio + a);
+#else
+    return audio[a];
+#endif
+}
+
+// ---------------------------------------------------------------- STFT pass A
+// Thread (half-warp hw, residue r = tid & 15) transforms the residue-r subsequences of frame f of two
+// slots (sa = warp + 16*half, sb = sa + 8) with one complex NQ-point FFT, applies W_N^{k1 r} and stores
+// Z_r[k1] for k1 < NQ into the exchange planes  Z[slot][k1*16 + r].
+template <bool SR16>
+SVAD_HD void stft_pass_a(const Tc& tc, float* sm, const Regs& rg, int f,
+                         const float* audio_a, const float* ctx_a, const float* audio_b, const float* ctx_b,
+                         long L, long t) {
+    using G = Geo<SR16>;
+    constexpr int NQ = G::NQ;
+    const int r = tc.tid & 15, half = (tc.tid >> 4) & 1;
+    const int sa = tc.warp + 16 * half, sb = sa + 8;
+    const float* win = sm + SmemMap::consts + SmemMap::c_win;
+    float zr[NQ], zi[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        int m = r + 16 * q;
+        float w = win[m];  // 0.5 * periodic Hann
+        zr[q] = audio_a ? w * window_sample<SR16>(audio_a, L, ctx_a, t, G::hop * f + m) : 0.0f;
+        zi[q] = audio_b ? w * window_sample<SR16>(audio_b, L, ctx_b, t, G::hop * f + m) : 0.0f;
+    }
+    fft_dif<NQ>(zr, zi);
+    float* za_re = sm + SmemMap::zre + sa * SmemMap::zpitch + r;
+    float* za_im = sm + SmemMap::zim + sa * SmemMap::zpitch + r;
+    float* zb_re = sm + SmemMap::zre + sb * SmemMap::zpitch + r;
+    float* zb_im = sm + SmemMap::zim + sb * SmemMap::zpitch + r;
+#pragma unroll
+    for (int k = 0; k < NQ; k++) {
+        constexpr int dummy = 0; (void)dummy;
+        const int pk = bitrev(k, ilog2(NQ)), pn = bitrev((NQ - k) % NQ, ilog2(NQ));
+        // Ya = Z[k] + conj(Z[-k]) ; Yb = -i (Z[k] - conj(Z[-k]))   (the 1/2 lives in the window)
+        float yar = zr[pk] + zr[pn], yai = zi[pk] - zi[pn];
+        float ybr = zi[pk] + zi[pn], ybi = zr[pn] - zr[pk];
+        float wr = rg.twr[k], wi = rg.twi[k];
+        za_re[k * 16] = yar * wr - yai * wi;
+        za_im[k * 16] = yar * wi + yai * wr;
+        zb_re[k * 16] = ybr * wr - ybi * wi;
+        zb_im[k * 16] = ybr * wi + ybi * wr;
+    }
+}
+
+// ---------------------------------------------------------------- STFT pass C
+// Thread (lane = slot) takes k1 and runs the 16-point DFT over r; bins k1 + NQ*k2, k2 < 8 (and N/2 for k1 = 0).
+template <bool SR16>
+SVAD_HD void stft_pass_c(const Tc& tc, float* sm, int f, int k1) {
+    using G = Geo<SR16>;
+    const int s = tc.lane;
+    const float* zre = sm + SmemMap::zre + s * SmemMap::zpitch + k1 * 16;
+    const float* zim = sm + SmemMap::zim + s * SmemMap::zpitch + k1 * 16;
+    float xr[16], xi[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) { xr[r] = zre[r]; xi[r] = zim[r]; }
+    fft_dif<16>(xr, xi);
+    float* mg = sm + SmemMap::mag + (f * G::F) * kSlots + s;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) {
+        const int p = bitrev(k2, 4);
+        mg[(k1 + G::NQ * k2) * kSlots] = sqrtf(xr[p] * xr[p] + xi[p] * xi[p]);
+    }
+    if (k1 == 0) {
+        const int p = bitrev(8, 4);
+        mg[(G::N / 2) * kSlots] = sqrtf(xr[p] * xr[p] + xi[p] * xi[p]);
+    }
+}
+
+// ---------------------------------------------------------------- helpers
+SVAD_HD void load8(const float* base, int row0, int row1, float (&x)[8]) {
+    f4 a = *reinterpret_cast<const f4*>(base + row0);
+    f4 b = *reinterpret_cast<const f4*>(base + row1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+SVAD_HD void store8(float* base, int row0, int row1, const float (&x)[8]) {
+    f4 a{x[0], x[1], x[2], x[3]}, b{x[4], x[5], x[6], x[7]};
+    *reinterpret_cast<f4*>(base + row0) = a;
+    *reinterpret_cast<f4*>(base + row1) = b;
+}
+SVAD_HD float relu(float v) { return v > 0.0f ? v : 0.0f; }   // NaN -> 0 like fmaxf(v, 0)
+SVAD_HD float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// ---------------------------------------------------------------- enc0
+// acc[t][i][u] (t<4 frames, i<8 rows, u<2 cols) -> rg.acc[(t*8+i)*2+u]; cols 16*warp + 2*ln + u.
+// slab = W0p[c][j][128] for channels [c0, c1).
+template <bool SR16, int RM>
+SVAD_HD void enc0_init(const Tc& tc, const float* sm, Regs& rg) {
+    const float* b0 = sm + SmemMap::consts + SmemMap::c_b0 + 16 * tc.warp + 2 * tc.ln;
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) { rg.acc[(t * 8 + i) * 2] = b0[0]; rg.acc[(t * 8 + i) * 2 + 1] = b0[1]; }
+}
+template <bool SR16, int RM>
+SVAD_HD void enc0_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int c0, int c1) {
+    using G = Geo<SR16>;
+    const int oc = 16 * tc.warp + 2 * tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const float* mag = sm + SmemMap::mag;
+#pragma unroll 1
+    for (int c = c0; c < c1; c++) {
+        float x[4][8];
+#pragma unroll
+        for (int f = 0; f < 4; f++) load8(mag + (f * G::F + c) * kSlots, r0, r1, x[f]);
+        const float* wp = slab + (c - c0) * 384 + oc;
+        f2 w[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) w[j] = *reinterpret_cast<const f2*>(wp + j * 128);
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int fi = t + j - 1;
+                if (fi < 0 || fi > 3) continue;
+#pragma unroll
+                for (int i = 0; i < RM; i++) {
+                    rg.acc[(t * 8 + i) * 2] = fmaf(w[j].x, x[fi][i], rg.acc[(t * 8 + i) * 2]);
+                    rg.acc[(t * 8 + i) * 2 + 1] = fmaf(w[j].y, x[fi][i], rg.acc[(t * 8 + i) * 2 + 1]);
+                }
+            }
+    }
+}
+template <bool SR16, int RM>
+SVAD_HD void enc0_store(const Tc& tc, float* sm, const Regs& rg) {
+    const int oc = 16 * tc.warp + 2 * tc.ln, r0 = tc.row0(), r1 = tc.row1();
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(rg.acc[(t * 8 + i) * 2 + u]) : 0.0f;
+            store8(sm + SmemMap::e0 + (t * 128 + oc + u) * kSlots, r0, r1, v);
+        }
+}
+
+// ---------------------------------------------------------------- enc1: 128 -> 64, stride 2, T 4 -> 2
+// acc[t][i] -> rg.acc[t*8+i]; col o = 8*warp + ln.  slab = W1p[c][j][64] for channels [c0, c1).
+// t=0 sees frames (-1,0,1) -> taps 1,2 ; t=1 sees frames (1,2,3).
+template <int RM>
+SVAD_HD void enc1_init(const Tc& tc, const float* sm, Regs& rg) {
+    float b = sm[SmemMap::consts + SmemMap::c_b1 + 8 * tc.warp + tc.ln];
+#pragma unroll
+    for (int k = 0; k < 16; k++) rg.acc[k] = b;
+}
+template <int RM>
+SVAD_HD void enc1_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int c0, int c1) {
+    const int o = 8 * tc.warp + tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const float* e0 = sm + SmemMap::e0;
+#pragma unroll 2
+    for (int c = c0; c < c1; c++) {
+        float x[4][8];
+#pragma unroll
+        for (int f = 0; f < 4; f++) load8(e0 + (f * 128 + c) * kSlots, r0, r1, x[f]);
+        const float* wp = slab + (c - c0) * 192 + o;
+        const float w0 = wp[0], w1 = wp[64], w2 = wp[128];
+#pragma unroll
+        for (int i = 0; i < RM; i++) {
+            rg.acc[i] = fmaf(w1, x[0][i], rg.acc[i]);
+            rg.acc[i] = fmaf(w2, x[1][i], rg.acc[i]);
+            rg.acc[8 + i] = fmaf(w0, x[1][i], rg.acc[8 + i]);
+            rg.acc[8 + i] = fmaf(w1, x[2][i], rg.acc[8 + i]);
+            rg.acc[8 + i] = fmaf(w2, x[3][i], rg.acc[8 + i]);
+        }
+    }
+}
+template <int RM>
+SVAD_HD void enc1_store(const Tc& tc, float* sm, const Regs& rg) {
+    const int o = 8 * tc.warp + tc.ln;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(rg.acc[t * 8 + i]) : 0.0f;
+        store8(sm + SmemMap::e1 + (t * 64 + o) * kSlots, tc.row0(), tc.row1(), v);
+    }
+}
+
+// ---------------------------------------------------------------- enc2: 64 -> 64, stride 2, T 2 -> 1 (taps 1,2 live)
+// slab = W2p[c][jj][64], jj=0 <-> tap 1 (frame 0), jj=1 <-> tap 2 (frame 1); one slab, 64 channels.
+template <int RM>
+SVAD_HD void enc2_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
+    const int o = 8 * tc.warp + tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    float b = sm[SmemMap::consts + SmemMap::c_b2 + o];
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = b;
+#pragma unroll 4
+    for (int c = 0; c < 64; c++) {
+        float x0[8], x1[8];
+        load8(sm + SmemMap::e1 + c * kSlots, r0, r1, x0);
+        load8(sm + SmemMap::e1 + (64 + c) * kSlots, r0, r1, x1);
+        const float w0 = slab[c * 128 + o], w1 = slab[c * 128 + 64 + o];
+#pragma unroll
+        for (int i = 0; i < RM; i++) { acc[i] = fmaf(w0, x0[i], acc[i]); acc[i] = fmaf(w1, x1[i], acc[i]); }
+    }
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(acc[i]) : 0.0f;
+    store8(sm + SmemMap::e2 + o * kSlots, r0, r1, v);
+    (void)rg;
+}
+
+// ---------------------------------------------------------------- enc3: 64 -> 128, T 1 -> 1 (tap 1 live)
+// slab = W3p[c][128]; cols 16*warp + 2*ln + u.
+template <int RM>
+SVAD_HD void enc3_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
+    const int oc = 16 * tc.warp + 2 * tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const float* b3 = sm + SmemMap::consts + SmemMap::c_b3 + oc;
+    float acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i][0] = b3[0]; acc[i][1] = b3[1]; }
+#pragma unroll 4
+    for (int c = 0; c < 64; c++) {
+        float x[8];
+        load8(sm + SmemMap::e2 + c * kSlots, r0, r1, x);
+        f2 w = *reinterpret_cast<const f2*>(slab + c * 128 + oc);
+#pragma unroll
+        for (int i = 0; i < RM; i++) { acc[i][0] = fmaf(w.x, x[i], acc[i][0]); acc[i][1] = fmaf(w.y, x[i], acc[i][1]); }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(acc[i][u]) : 0.0f;
+        store8(sm + SmemMap::e3 + (oc + u) * kSlots, r0, r1, v);
+    }
+    (void)rg;
+}
+
+// ---------------------------------------------------------------- LSTM
+// Columns are permuted on the host: n' = 64*warp + 32*u + 4*ln + g  <->  gate g of hidden unit j = 16*warp + 2*ln + u.
+// acc[i][u*4+g] -> rg.acc[i*8 + u*4 + g].  slab = Wl[k][512] for k in [k0, k0+16); k < 128 reads e3, else h.
+template <int RM>
+SVAD_HD void lstm_init(const Tc& tc, const float* sm, Regs& rg) {
+    const float* bl = sm + SmemMap::consts + SmemMap::c_bl + 64 * tc.warp + 4 * tc.ln;
+    f4 b0 = *reinterpret_cast<const f4*>(bl), b1 = *reinterpret_cast<const f4*>(bl + 32);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        rg.acc[i * 8 + 0] = b0.x; rg.acc[i * 8 + 1] = b0.y; rg.acc[i * 8 + 2] = b0.z; rg.acc[i * 8 + 3] = b0.w;
+        rg.acc[i * 8 + 4] = b1.x; rg.acc[i * 8 + 5] = b1.y; rg.acc[i * 8 + 6] = b1.z; rg.acc[i * 8 + 7] = b1.w;
+    }
+}
+template <int RM>
+SVAD_HD void lstm_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int k0) {
+    const int nc = 64 * tc.warp + 4 * tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const float* a = (k0 < kHid) ? sm + SmemMap::e3 + k0 * kSlots : sm + SmemMap::h + (k0 - kHid) * kSlots;
+#pragma unroll 4
+    for (int kk = 0; kk < 16; kk++) {
+        float x[8];
+        load8(a + kk * kSlots, r0, r1, x);
+        f4 w0 = *reinterpret_cast<const f4*>(slab + kk * kGates + nc);
+        f4 w1 = *reinterpret_cast<const f4*>(slab + kk * kGates + nc + 32);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < RM; i++)
+#pragma unroll
+            for (int n = 0; n < 8; n++) rg.acc[i * 8 + n] = fmaf(w[n], x[i], rg.acc[i * 8 + n]);
+    }
+}
+// gate nonlinearity + state update; writes h' into smem (after the barrier that ends the last slab).
+template <int RM>
+SVAD_HD void lstm_epilogue(const Tc& tc, float* sm, Regs& rg) {
+    const int j0 = 16 * tc.warp + 2 * tc.ln;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        float hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i < RM) {
+                const float* g = rg.acc + i * 8 + u * 4;
+                float ig = sigmoid_acc(g[0]), fg = sigmoid_acc(g[1]), gg = tanhf(g[2]), og = sigmoid_acc(g[3]);
+                float cn = fmaf(fg, rg.c[i * 2 + u], ig * gg);
+                rg.c[i * 2 + u] = cn;
+                hv[i] = og * tanhf(cn);
+            } else {
+                hv[i] = 0.0f;
+            }
+        }
+        store8(sm + SmemMap::h + (j0 + u) * kSlots, tc.row0(), tc.row1(), hv);
+    }
+}
+// head: thread tid < 32 (slot = tid): p = sigmoid(sum_j wout[j] relu(h'[j]) + bout)
+SVAD_HD float head_prob(const float* sm, int slot) {
+    const float* wout = sm + SmemMap::consts + SmemMap::c_wout;
+    const float* h = sm + SmemMap::h + slot;
+    float a0 = sm[SmemMap::consts + SmemMap::c_bout], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < kHid; j += 4) {
+        a0 = fmaf(wout[j], relu(h[j * kSlots]), a0);
+        a1 = fmaf(wout[j + 1], relu(h[(j + 1) * kSlots]), a1);
+        a2 = fmaf(wout[j + 2], relu(h[(j + 2) * kSlots]), a2);
+        a3 = fmaf(wout[j + 3], relu(h[(j + 3) * kSlots]), a3);
+    }
+    return sigmoid_acc((a0 + a1) + (a2 + a3));
+}
+
+}  // namespace svad

@@ -1,0 +1,156 @@
+// svad_pack.h -- host side: read the SVADW001 weight container and lay the parameters out as the
+// "weight tape" the fused kernel streams through shared memory once per chunk step.
+//
+// Tape (fp32, consumption order; every slab is a contiguous, 16-byte aligned byte range):
+//   enc0  W0p[c][j][o]    c < F, j < 3, o < 128          (= encoder.0.reparam_conv.weight[o][c][j])
+//   enc1  W1p[c][j][o]    c < 128, j < 3, o < 64
+//   enc2  W2p[c][jj][o]   c < 64, jj < 2 (taps 1,2: tap 0 only ever multiplies zero padding), o < 64
+//   enc3  W3p[c][o]       c < 64, tap 1 only, o < 128
+//   lstm  Wl[k][n']       k < 256 ([W_ih ; W_hh] along k), n' = 64*w + 32*u + 4*l + g  <->  row g*128 + j of
+//                         the PyTorch LSTMCell weights with j = 16*w + 2*l + u (gate order i,f,g,o)
+// Constants block (loaded into shared memory once per CTA), see svad::SmemMap::c_*:
+//   b0[128] b1[64] b2[64] b3[128] bl[512] (= b_ih + b_hh, permuted like n') wout[128] bout pad[3] win[256]
+//   win[m] = 0.5 * (0.5 - 0.5 cos(2 pi m / N))   (periodic Hann; the 1/2 belongs to the two-for-one FFT split)
+// Reference for the parameter names: silero_vad.jit state_dict.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "svad_core.h"
+
+namespace svad {
+
+struct HostTensor { std::vector<uint32_t> dims; std::vector<float> data; };
+using TensorMap = std::map<std::string, HostTensor>;
+
+inline bool read_container(const char* path, TensorMap& out, std::string& err) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { err = std::string("cannot open ") + path; return false; }
+    char magic[8]; uint32_t n = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "SVADW001", 8) || fread(&n, 4, 1, f) != 1) { fclose(f); err = "bad magic"; return false; }
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t nl = 0, nd = 0;
+        if (fread(&nl, 4, 1, f) != 1 || nl > 255) { fclose(f); err = "bad name"; return false; }
+        std::string name(nl, 0);
+        if (fread(&name[0], 1, nl, f) != nl || fread(&nd, 4, 1, f) != 1 || nd > 4) { fclose(f); err = "bad tensor header"; return false; }
+        HostTensor t; t.dims.resize(nd); size_t numel = 1;
+        for (uint32_t d = 0; d < nd; d++) { if (fread(&t.dims[d], 4, 1, f) != 1) { fclose(f); err = "bad dims"; return false; } numel *= t.dims[d]; }
+        t.data.resize(numel);
+        if (fread(t.data.data(), 4, numel, f) != numel) { fclose(f); err = "truncated"; return false; }
+        out[name] = std::move(t);
+    }
+    fclose(f);
+    return true;
+}
+
+// ---- static slab schedule (shared by host packer, kernel and emulator)
+template <bool SR16>
+struct Tape {
+    using G = Geo<SR16>;
+    static constexpr int e0_off = 0;
+    static constexpr int e1_off = e0_off + G::F * 384;
+    static constexpr int e2_off = e1_off + 128 * 192;
+    static constexpr int e3_off = e2_off + 64 * 128;
+    static constexpr int l_off = e3_off + 64 * 128;
+    static constexpr int total = l_off + 256 * 512;
+    // enc0 slab s covers channels [e0_c0(s), e0_c0(s+1))
+    SVAD_HD static constexpr int e0_c0(int s) {
+        return s * (G::F / G::e0_nslab) + (s < G::F % G::e0_nslab ? s : G::F % G::e0_nslab);
+    }
+    // slab index -> (float offset, float count)
+    SVAD_HD static constexpr int slab_off(int i) {
+        if (i < G::e0_nslab) return e0_off + e0_c0(i) * 384;
+        i -= G::e0_nslab;
+        if (i < 4) return e1_off + i * 32 * 192;
+        i -= 4;
+        if (i == 0) return e2_off;
+        if (i == 1) return e3_off;
+        i -= 2;
+        return l_off + i * 16 * 512;
+    }
+    SVAD_HD static constexpr int slab_len(int i) {
+        if (i < G::e0_nslab) return (e0_c0(i + 1) - e0_c0(i)) * 384;
+        i -= G::e0_nslab;
+        if (i < 4) return 32 * 192;
+        i -= 4;
+        if (i < 2) return 64 * 128;
+        return 16 * 512;
+    }
+};
+
+struct PackedBranch {
+    std::vector<float> tape;
+    std::vector<float> consts;
+};
+
+template <bool SR16>
+inline bool pack_branch(const TensorMap& tm, PackedBranch& out, std::string& err) {
+    using G = Geo<SR16>;
+    using T = Tape<SR16>;
+    const std::string p = SR16 ? "_model." : "_model_8k.";
+    auto get = [&](const char* s, std::vector<uint32_t> dims) -> const float* {
+        auto it = tm.find(p + s);
+        if (it == tm.end()) { err = "missing tensor " + p + s; return nullptr; }
+        if (it->second.dims != dims) { err = "unexpected shape for " + p + s; return nullptr; }
+        return it->second.data.data();
+    };
+    const uint32_t F = G::F;
+    const float* w0 = get("encoder.0.reparam_conv.weight", {128, F, 3});
+    const float* b0 = get("encoder.0.reparam_conv.bias", {128});
+    const float* w1 = get("encoder.1.reparam_conv.weight", {64, 128, 3});
+    const float* b1 = get("encoder.1.reparam_conv.bias", {64});
+    const float* w2 = get("encoder.2.reparam_conv.weight", {64, 64, 3});
+    const float* b2 = get("encoder.2.reparam_conv.bias", {64});
+    const float* w3 = get("encoder.3.reparam_conv.weight", {128, 64, 3});
+    const float* b3 = get("encoder.3.reparam_conv.bias", {128});
+    const float* wih = get("decoder.rnn.weight_ih", {512, 128});
+    const float* whh = get("decoder.rnn.weight_hh", {512, 128});
+    const float* bih = get("decoder.rnn.bias_ih", {512});
+    const float* bhh = get("decoder.rnn.bias_hh", {512});
+    const float* wo = get("decoder.decoder.2.weight", {1, 128, 1});
+    const float* bo = get("decoder.decoder.2.bias", {1});
+    if (!w0 || !b0 || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !wih || !whh || !bih || !bhh || !wo || !bo) return false;
+
+    out.tape.assign(T::total, 0.0f);
+    float* t = out.tape.data();
+    for (int c = 0; c < G::F; c++)
+        for (int j = 0; j < 3; j++)
+            for (int o = 0; o < 128; o++) t[T::e0_off + (c * 3 + j) * 128 + o] = w0[(o * G::F + c) * 3 + j];
+    for (int c = 0; c < 128; c++)
+        for (int j = 0; j < 3; j++)
+            for (int o = 0; o < 64; o++) t[T::e1_off + (c * 3 + j) * 64 + o] = w1[(o * 128 + c) * 3 + j];
+    for (int c = 0; c < 64; c++)
+        for (int jj = 0; jj < 2; jj++)
+            for (int o = 0; o < 64; o++) t[T::e2_off + (c * 2 + jj) * 64 + o] = w2[(o * 64 + c) * 3 + (jj + 1)];
+    for (int c = 0; c < 64; c++)
+        for (int o = 0; o < 128; o++) t[T::e3_off + c * 128 + o] = w3[(o * 64 + c) * 3 + 1];
+    out.consts.assign(SmemMap::consts_floats, 0.0f);
+    float* cs = out.consts.data();
+    for (int w = 0; w < 8; w++)
+        for (int u = 0; u < 2; u++)
+            for (int l = 0; l < 8; l++)
+                for (int g = 0; g < 4; g++) {
+                    const int np = 64 * w + 32 * u + 4 * l + g, j = 16 * w + 2 * l + u, row = g * 128 + j;
+                    for (int k = 0; k < 128; k++) {
+                        t[T::l_off + k * 512 + np] = wih[row * 128 + k];
+                        t[T::l_off + (128 + k) * 512 + np] = whh[row * 128 + k];
+                    }
+                    cs[SmemMap::c_bl + np] = bih[row] + bhh[row];
+                }
+    memcpy(cs + SmemMap::c_b0, b0, 128 * 4);
+    memcpy(cs + SmemMap::c_b1, b1, 64 * 4);
+    memcpy(cs + SmemMap::c_b2, b2, 64 * 4);
+    memcpy(cs + SmemMap::c_b3, b3, 128 * 4);
+    memcpy(cs + SmemMap::c_wout, wo, 128 * 4);
+    cs[SmemMap::c_bout] = bo[0];
+    for (int m = 0; m < G::N; m++)
+        cs[SmemMap::c_win + m] = (float)(0.5 * (0.5 - 0.5 * cos(2.0 * M_PI * (double)m / (double)G::N)));
+    return true;
+}
+
+}  // namespace svad

@@ -1,0 +1,188 @@
+// svad_tile.h -- barrier-level schedule of one CTA of the fused fp32 kernel: a tile of up to 4*RM
+// streams is carried through all T chunk steps; (h, c) and the audio context never leave the SM.
+//
+// `Env` hides what differs between the GPU and the CPU emulator:
+//   int tid();  float* smem();  void sync();                      CTA barrier
+//   const float* slab_acquire(long it);                           wait until tape slab #it is in its stage
+//   void slab_release(long it, long total);                       (after a sync) thread 0 refills the stage
+// Per step and tile: 8 barriers for the STFT, one per weight slab, 3 around the LSTM epilogue / head.
+#pragma once
+#include "svad_core.h"
+#include "svad_pack.h"
+
+namespace svad {
+
+struct TileArgs {
+    const float* audio;     // [B][ld] fp32, device (or host in the emulator)
+    long ld, L;             // row stride, valid samples per row (tail is zero-padded to T*n)
+    int B;                  // streams
+    long T;                 // chunk steps = ceil(L / n)
+    const float* state_in;  // [2][B][128] or null (zeros)
+    const float* ctx_in;    // [B] rows of ctx floats, row stride ctx_ld, or null (zeros)
+    long ctx_ld;
+    float* state_out;       // [2][B][128] or null
+    float* ctx_out;         // [B][ctx] or null
+    float* probs;           // [B][ldp]
+    long ldp;
+    const float* tape;      // weight tape (Tape<SR16>::total floats)
+    const float* consts;    // SmemMap::consts_floats floats
+};
+
+template <bool SR16, int RM, class Env>
+SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_stride, int ntiles) {
+    using G = Geo<SR16>;
+    using TP = Tape<SR16>;
+    const Tc tc(env.tid());
+    float* sm = env.smem();
+    Regs rg;
+    constexpr int BT = 4 * RM;
+
+    // constants -> smem, pass-A twiddles -> registers
+    for (int i = tc.tid; i < SmemMap::consts_floats; i += kThreads) sm[SmemMap::consts + i] = a.consts[i];
+    {
+        const int r = tc.tid & 15;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (k < G::NQ) {
+                float s, c;
+                const float x = -2.0f * (float)((k * r) % G::N) / (float)G::N;  // angle / pi
+#if defined(__CUDA_ARCH__)
+                sincospif(x, &s, &c);
+#else
+                s = (float)sin(M_PI * (double)x); c = (float)cos(M_PI * (double)x);
+#endif
+                rg.twr[k] = c; rg.twi[k] = s;
+            } else { rg.twr[k] = 1.0f; rg.twi[k] = 0.0f; }
+        }
+    }
+    int my_tiles = 0;
+    for (int tile = first_tile; tile < ntiles; tile += tile_stride) my_tiles++;
+    const long total_slabs = (long)my_tiles * a.T * G::nslab;
+    long it = 0;  // running slab counter of this CTA
+
+    for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
+        const int g0 = tile * BT;
+        // ---- tile init: h -> smem, c -> registers
+        env.sync();  // previous tile's readers of h / consts writers done
+        for (int i = tc.tid; i < kHid * kSlots; i += kThreads) {
+            const int j = i >> 5, s = i & 31;
+            const int g = g0 + slot_to_local<RM>(s);
+            float v = 0.0f;
+            if (a.state_in && slot_valid<RM>(s) && g < a.B) v = a.state_in[(long)g * kHid + j];
+            sm[SmemMap::h + i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int s = (i < 4) ? tc.row0() + i : tc.row1() + (i - 4);
+                const int g = g0 + slot_to_local<RM>(s);
+                const int j = 16 * tc.warp + 2 * tc.ln + u;
+                float v = 0.0f;
+                if (a.state_in && i < RM && g < a.B) v = a.state_in[((long)a.B + g) * kHid + j];
+                rg.c[i * 2 + u] = v;
+            }
+        // audio rows of the two slots this thread feeds in STFT pass A
+        const int half = (tc.tid >> 4) & 1;
+        const int sa = tc.warp + 16 * half, sb = sa + 8;
+        const int ga = g0 + slot_to_local<RM>(sa), gb = g0 + slot_to_local<RM>(sb);
+        const bool va = slot_valid<RM>(sa) && ga < a.B, vb = slot_valid<RM>(sb) && gb < a.B;
+        const float* aud_a = va ? a.audio + (long)ga * a.ld : nullptr;
+        const float* aud_b = vb ? a.audio + (long)gb * a.ld : nullptr;
+        const float* cx_a = (va && a.ctx_in) ? a.ctx_in + (long)ga * a.ctx_ld : nullptr;
+        const float* cx_b = (vb && a.ctx_in) ? a.ctx_in + (long)gb * a.ctx_ld : nullptr;
+        env.sync();
+
+        for (long t = 0; t < a.T; t++) {
+            // ---------------- STFT
+#pragma unroll 1
+            for (int f = 0; f < 4; f++) {
+                stft_pass_a<SR16>(tc, sm, rg, f, aud_a, cx_a, aud_b, cx_b, a.L, t);
+                env.sync();
+#pragma unroll
+                for (int kk = 0; kk < G::NQ / 8; kk++) stft_pass_c<SR16>(tc, sm, f, tc.warp * (G::NQ / 8) + kk);
+                env.sync();
+            }
+            // ---------------- enc0
+            enc0_init<SR16, RM>(tc, sm, rg);
+#pragma unroll 1
+            for (int s = 0; s < G::e0_nslab; s++, it++) {
+                const float* slab = env.slab_acquire(it);
+                enc0_slab<SR16, RM>(tc, sm, slab, rg, TP::e0_c0(s), TP::e0_c0(s + 1));
+                if (s == G::e0_nslab - 1) enc0_store<SR16, RM>(tc, sm, rg);
+                env.sync();
+                env.slab_release(it, total_slabs);
+            }
+            // ---------------- enc1
+            enc1_init<RM>(tc, sm, rg);
+#pragma unroll 1
+            for (int s = 0; s < 4; s++, it++) {
+                const float* slab = env.slab_acquire(it);
+                enc1_slab<RM>(tc, sm, slab, rg, s * 32, s * 32 + 32);
+                if (s == 3) enc1_store<RM>(tc, sm, rg);
+                env.sync();
+                env.slab_release(it, total_slabs);
+            }
+            // ---------------- enc2, enc3
+            {
+                const float* slab = env.slab_acquire(it);
+                enc2_all<RM>(tc, sm, slab, rg);
+                env.sync();
+                env.slab_release(it, total_slabs);
+                it++;
+                slab = env.slab_acquire(it);
+                enc3_all<RM>(tc, sm, slab, rg);
+                env.sync();
+                env.slab_release(it, total_slabs);
+                it++;
+            }
+            // ---------------- LSTM + head
+            lstm_init<RM>(tc, sm, rg);
+#pragma unroll 1
+            for (int s = 0; s < 16; s++, it++) {
+                const float* slab = env.slab_acquire(it);
+                lstm_slab<RM>(tc, sm, slab, rg, s * 16);
+                env.sync();
+                env.slab_release(it, total_slabs);
+            }
+            lstm_epilogue<RM>(tc, sm, rg);
+            env.sync();
+            if (tc.tid < kSlots) {
+                const int g = g0 + slot_to_local<RM>(tc.tid);
+                if (slot_valid<RM>(tc.tid) && g < a.B) a.probs[(long)g * a.ldp + t] = head_prob(sm, tc.tid);
+            }
+        }
+        // ---- tile exit: carry state / context out
+        env.sync();
+        if (a.state_out) {
+            for (int i = tc.tid; i < kHid * kSlots; i += kThreads) {
+                const int s = i & 31, j = i >> 5;
+                const int g = g0 + slot_to_local<RM>(s);
+                if (slot_valid<RM>(s) && g < a.B) a.state_out[(long)g * kHid + j] = sm[SmemMap::h + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int s = (i < 4) ? tc.row0() + i : tc.row1() + (i - 4);
+                    const int g = g0 + slot_to_local<RM>(s);
+                    const int j = 16 * tc.warp + 2 * tc.ln + u;
+                    if (i < RM && g < a.B) a.state_out[((long)a.B + g) * kHid + j] = rg.c[i * 2 + u];
+                }
+        }
+        if (a.ctx_out) {
+            for (int i = tc.tid; i < BT * G::ctx; i += kThreads) {
+                const int loc = i / G::ctx, k = i % G::ctx, g = g0 + loc;
+                if (g < a.B) {
+                    // new context = last ctx samples of the (zero-padded) final window
+                    const float* cx = a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr;
+                    float v = (a.T > 0) ? window_sample<SR16>(a.audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k)
+                                        : (cx ? cx[k] : 0.0f);
+                    a.ctx_out[(long)g * G::ctx + k] = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace svad

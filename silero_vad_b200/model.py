@@ -1,0 +1,151 @@
+"""Model object with the reference's duck-typed surface, backed by the CUDA engine.
+
+Mirrors (same names, argument meaning, error types and messages):
+  load_silero_vad()                       /root/reference/src/silero_vad/model.py:6-36
+  model(x, sr), reset_states(),           silero_vad.jit::forward / reset_states / audio_forward and the
+  audio_forward(x, sr), _validate_input   readable twin OnnxWrapper, src/silero_vad/utils_vad.py:33-110
+PyTorch is used for device memory and streams only; all arithmetic happens in libsilero_vad_b200.so.
+There is no CPU path: constructing the model without a CUDA device raises.
+"""
+from pathlib import Path
+
+import torch
+
+from . import _cabi
+
+WEIGHTS = Path(__file__).resolve().parent / "data" / "silero_vad_v6.weights"
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class SileroVADB200:
+    sample_rates = [8000, 16000]
+
+    def __init__(self, device=None, weights=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("silero_vad_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.engine = _cabi.Engine(weights or WEIGHTS, self.device.index)
+        self.reset_states()
+
+    # ------------------------------------------------------------------ reference surface
+    def reset_states(self, batch_size=1):
+        """Forget (h, c), the audio context, the last sr and batch size (utils_vad.py:51-55)."""
+        self._state = None      # f32[2, B, 128] on device
+        self._context = None    # f32[B, ctx] on device
+        self._last_sr = 0
+        self._last_batch_size = 0
+
+    def _validate_input(self, x, sr: int):
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(x)
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        if x.dim() > 2:
+            raise ValueError(f"Too many dimensions for input audio chunk {x.dim()}")
+        if sr != 16000 and (sr % 16000 == 0):
+            step = sr // 16000
+            x = x[:, ::step]
+            sr = 16000
+        if sr not in self.sample_rates:
+            raise ValueError(f"Supported sampling rates: {self.sample_rates} (or multiply of 16000)")
+        if sr / x.shape[1] > 31.25:
+            raise ValueError("Input audio chunk is too short")
+        return x, sr
+
+    def _to_device(self, x):
+        return x.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    def __call__(self, x, sr: int):
+        x, sr = self._validate_input(x, sr)
+        num_samples = 512 if sr == 16000 else 256
+        if x.shape[-1] != num_samples:
+            raise ValueError(f"Provided number of samples is {x.shape[-1]} (Supported values: 256 for 8000 sample rate, 512 for 16000)")
+        batch_size = x.shape[0]
+        context_size = 64 if sr == 16000 else 32
+        if self._last_sr and self._last_sr != sr:
+            self.reset_states()
+        if self._last_batch_size and self._last_batch_size != batch_size:
+            self.reset_states()
+        in_device = x.device
+        with torch.cuda.device(self.device):
+            xd = self._to_device(x)
+            if self._state is None:
+                self._state = torch.zeros(2, batch_size, 128, device=self.device)
+            if self._context is None:
+                self._context = torch.zeros(batch_size, context_size, device=self.device)
+            out = torch.empty(batch_size, 1, device=self.device)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            # one chunk: state and context are read, advanced and written back in place by the kernel
+            self.engine.forward_device(sr, batch_size, num_samples, num_samples, _ptr(xd), _ptr(self._state), _ptr(self._context),
+                                       _ptr(self._state), _ptr(self._context), _ptr(out), 1, st)
+        self._last_sr = sr
+        self._last_batch_size = batch_size
+        return out if in_device == self.device else out.to(in_device)
+
+    forward = __call__
+
+    def audio_forward(self, x, sr: int):
+        """All chunk probabilities of B streams in one fused launch -> f32[B, ceil(L/n)] on the CPU
+        (utils_vad.py:94-110: validate, reset, zero-pad the tail, loop, cat, .cpu())."""
+        return self.audio_forward_device(x, sr).cpu()
+
+    # ------------------------------------------------------------------ extensions
+    def audio_forward_device(self, x, sr: int, reset=True):
+        """Like audio_forward but leaves the probabilities on the GPU; with reset=False continues from the
+        carried state/context (long streams fed in pieces whose length is a multiple of the chunk size)."""
+        x, sr = self._validate_input(x, sr)
+        if reset:
+            self.reset_states()
+        n = 512 if sr == 16000 else 256
+        ctx = 64 if sr == 16000 else 32
+        B, L = x.shape
+        T = (L + n - 1) // n
+        if self._last_sr and self._last_sr != sr:
+            self.reset_states()
+        if self._last_batch_size and self._last_batch_size != B:
+            self.reset_states()
+        with torch.cuda.device(self.device):
+            xd = self._to_device(x)
+            if self._state is None:
+                self._state = torch.zeros(2, B, 128, device=self.device)
+            if self._context is None:
+                self._context = torch.zeros(B, ctx, device=self.device)
+            probs = torch.empty(B, T, device=self.device)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            self.engine.forward_device(sr, B, L, xd.stride(0), _ptr(xd), _ptr(self._state), _ptr(self._context), _ptr(self._state),
+                                       _ptr(self._context), _ptr(probs), max(T, 1), st)
+        self._last_sr = sr
+        self._last_batch_size = B
+        return probs
+
+    def get_states(self):
+        """(state f32[2,B,128], context f32[B,ctx]) clones, to park a set of streams."""
+        return (None if self._state is None else self._state.clone(), None if self._context is None else self._context.clone(),
+                self._last_sr, self._last_batch_size)
+
+    def set_states(self, saved):
+        self._state, self._context, self._last_sr, self._last_batch_size = saved
+
+    def eval(self):
+        return self
+
+    def to(self, *args, **kwargs):
+        return self
+
+
+def load_silero_vad(onnx=False, opset_version=16, device=None):
+    """Drop-in for silero_vad.load_silero_vad (model.py:6-36).  `onnx` / `opset_version` select between
+    files that hold the same network in the reference; here they only keep the reference's argument
+    checking (unknown opset with onnx=True raises) -- every variant runs the CUDA engine."""
+    available_ops = [15, 16]
+    if onnx and opset_version not in available_ops:
+        raise Exception(f'Available ONNX opset_version: {available_ops}')
+    model = SileroVADB200(device=device)
+    if onnx and opset_version == 15:
+        model.sample_rates = [16000]   # silero_vad_16k_op15.onnx is 16 kHz only (utils_vad.py:27-29)
+    return model

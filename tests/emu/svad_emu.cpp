@@ -1,0 +1,86 @@
+// svad_emu.cpp -- CPU emulator of one CTA of the fused fp32 kernel (TEST INFRASTRUCTURE).
+// Runs svad::run_cta<> (the exact schedule + per-thread arithmetic the CUDA kernel compiles) on 256
+// OS threads with a pthread barrier standing in for __syncthreads and memcpy standing in for the
+// TMA bulk copies of weight slabs.  Lets the layout / index algebra be checked against the oracle
+// in the build container, which has no GPU.  Not part of the product; never timed.
+#include <pthread.h>
+
+#include <cstdlib>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../silero_vad_b200/csrc/svad_tile.h"
+
+using namespace svad;
+
+namespace {
+struct Shared {
+    std::vector<float> smem;
+    pthread_barrier_t bar;
+    const float* tape;
+};
+template <bool SR16>
+struct EmuEnv {
+    Shared* sh;
+    int tid_;
+    int tid() const { return tid_; }
+    float* smem() { return sh->smem.data(); }
+    void sync() { pthread_barrier_wait(&sh->bar); }
+    void issue(long it) {
+        const int idx = (int)(it % Geo<SR16>::nslab), stage = (int)(it % kStages);
+        memcpy(sh->smem.data() + SmemMap::stage + stage * SmemMap::stage_floats, sh->tape + Tape<SR16>::slab_off(idx),
+               sizeof(float) * Tape<SR16>::slab_len(idx));
+    }
+    const float* slab_acquire(long it) { return sh->smem.data() + SmemMap::stage + (it % kStages) * SmemMap::stage_floats; }
+    void slab_release(long it, long total) {
+        if (tid_ == 0 && it + kStages < total) issue(it + kStages);
+    }
+};
+
+template <bool SR16, int RM>
+void run(const TileArgs& a, int ntiles) {
+    Shared sh;
+    sh.smem.assign(SmemMap::total_floats, 0.0f);
+    sh.tape = a.tape;
+    pthread_barrier_init(&sh.bar, nullptr, kThreads);
+    {
+        EmuEnv<SR16> e0{&sh, 0};
+        const long total = (long)ntiles * a.T * Geo<SR16>::nslab;
+        for (long i = 0; i < kStages && i < total; i++) e0.issue(i);
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < kThreads; t++)
+        th.emplace_back([&, t] {
+            EmuEnv<SR16> env{&sh, t};
+            run_cta<SR16, RM>(env, a, 0, 1, ntiles);
+        });
+    for (auto& x : th) x.join();
+    pthread_barrier_destroy(&sh.bar);
+}
+}  // namespace
+
+extern "C" int svad_emu_forward(const char* weights, int sr, int rm, int B, long L, const float* audio, const float* state_in,
+                                const float* ctx_in, float* state_out, float* ctx_out, float* probs) {
+    TensorMap tm;
+    std::string err;
+    if (!read_container(weights, tm, err)) return -1;
+    PackedBranch pb;
+    const bool sr16 = sr == 16000;
+    if (!(sr16 ? pack_branch<true>(tm, pb, err) : pack_branch<false>(tm, pb, err))) return -2;
+    const int n = sr16 ? 512 : 256;
+    TileArgs a{};
+    a.audio = audio; a.ld = L; a.L = L; a.B = B; a.T = (L + n - 1) / n;
+    a.state_in = state_in; a.ctx_in = ctx_in; a.ctx_ld = sr16 ? 64 : 32; a.state_out = state_out; a.ctx_out = ctx_out;
+    a.probs = probs; a.ldp = a.T; a.tape = pb.tape.data(); a.consts = pb.consts.data();
+    const int bt = 4 * rm, ntiles = (B + bt - 1) / bt;
+    switch (rm * 2 + (sr16 ? 1 : 0)) {
+        case 9: run<true, 4>(a, ntiles); break;   case 8: run<false, 4>(a, ntiles); break;
+        case 11: run<true, 5>(a, ntiles); break;  case 10: run<false, 5>(a, ntiles); break;
+        case 13: run<true, 6>(a, ntiles); break;  case 12: run<false, 6>(a, ntiles); break;
+        case 15: run<true, 7>(a, ntiles); break;  case 14: run<false, 7>(a, ntiles); break;
+        case 17: run<true, 8>(a, ntiles); break;  case 16: run<false, 8>(a, ntiles); break;
+        default: return -3;
+    }
+    return 0;
+}

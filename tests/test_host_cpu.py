@@ -1,0 +1,142 @@
+"""CPU-only tests of the product's host side: the C ABI library loads and exports every symbol the header
+declares, the C++ segment automaton equals the reference on scripted probabilities, the barrier-level CPU
+emulation of the fused kernel (same source as the CUDA kernel) matches the oracle, argument validation."""
+import ctypes
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+
+def test_cabi_exports_every_declared_symbol():
+    from silero_vad_b200 import _cabi
+    L = _cabi.lib()
+    header = (REPO / "include" / "silero_vad_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(svad_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(_cabi.EXPORTS) == declared
+    assert L.svad_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device the engine must refuse to construct (no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from silero_vad_b200 import _cabi, load_silero_vad
+    from silero_vad_b200.model import WEIGHTS
+    with pytest.raises(RuntimeError):
+        load_silero_vad()
+    with pytest.raises(_cabi.SvadError):
+        _cabi.Engine(WEIGHTS, 0)
+    with pytest.raises(Exception):
+        load_silero_vad(onnx=True, opset_version=14)
+
+
+def test_product_does_not_touch_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may use oracle/."""
+    for p in (REPO / "silero_vad_b200").rglob("*"):
+        if p.suffix in {".py", ".cu", ".h", ".cpp"}:
+            assert "oracle" not in p.read_text(), p
+
+
+def _params(kw, sr):
+    from silero_vad_b200.utils_vad import _segment_params
+    d = dict(threshold=0.5, neg_threshold=None, min_speech_duration_ms=250, max_speech_duration_s=float("inf"),
+             min_silence_duration_ms=100, speech_pad_ms=30, min_silence_at_max_speech=98, use_max_poss_sil_at_max_speech=True)
+    d.update(kw)
+    return _segment_params(sr, **d)
+
+
+def test_segments_cpp_equals_reference_cases(sm_cases):
+    from silero_vad_b200 import _cabi
+    from silero_vad_b200.utils_vad import _finish
+    for c in sm_cases:
+        sr = c["sampling_rate"]
+        step = sr // 16000 if sr > 16000 else 1
+        msr = 16000 if sr >= 16000 else sr
+        kw = dict(c["kwargs"])
+        rs, tr = kw.pop("return_seconds", False), kw.pop("time_resolution", 1)
+        alen = c["audio_len"] // step
+        segs = _cabi.speech_segments(np.asarray(c["probs"], np.float32)[None], np.asarray([alen]), _params(kw, msr))[0]
+        out = _finish(segs, msr, alen, rs, tr, step)
+        assert [[d["start"], d["end"]] for d in out] == c["segments"], c["kwargs"]
+
+
+def test_segments_cpp_equals_oracle_random_batch():
+    """Batched call on random probability tracks vs the pure-Python restatement, many parameter sets."""
+    from oracle import oracle as O
+    from silero_vad_b200 import _cabi
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        sr = int(rng.choice([16000, 8000]))
+        w = 512 if sr == 16000 else 256
+        B, T = int(rng.integers(1, 9)), int(rng.integers(1, 300))
+        probs = np.clip(np.cumsum(rng.normal(0, 0.25, (B, T)), axis=1) % 2.0, 0, 1).astype(np.float32)
+        lens = np.array([int(rng.integers(1, T * w + 1)) for _ in range(B)])
+        kw = dict(threshold=float(rng.choice([0.5, 0.35, 0.8])), min_speech_duration_ms=int(rng.choice([0, 250, 700])),
+                  min_silence_duration_ms=int(rng.choice([0, 100, 400])), speech_pad_ms=int(rng.choice([0, 30, 150])),
+                  max_speech_duration_s=float(rng.choice([float("inf"), 1.5, 3.0])),
+                  use_max_poss_sil_at_max_speech=bool(rng.integers(0, 2)), min_silence_at_max_speech=int(rng.choice([98, 10])))
+        got = _cabi.speech_segments(probs, lens, _params(kw, sr))
+        for b in range(B):
+            Tb = (lens[b] + w - 1) // w
+            want = O.get_speech_timestamps(probs[b, :Tb].tolist(), int(lens[b]), sampling_rate=sr, **kw)
+            assert got[b] == [(d["start"], d["end"]) for d in want], (trial, b, kw)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = REPO / "tests" / "emu" / "libsvad_emu.so"
+    src = REPO / "tests" / "emu" / "svad_emu.cpp"
+    deps = [src] + list((REPO / "silero_vad_b200" / "csrc").glob("*.h"))
+    if not so.exists() or any(d.stat().st_mtime > so.stat().st_mtime for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", str(so), str(src)], check=True)
+    lib = ctypes.CDLL(str(so))
+    fp = ctypes.c_void_p
+    lib.svad_emu_forward.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long, fp, fp, fp, fp, fp, fp]
+    return lib
+
+
+@pytest.mark.parametrize("sr,rm,B", [(16000, 8, 5), (16000, 7, 37), (8000, 8, 5), (8000, 5, 23), (16000, 4, 1)])
+def test_emulated_kernel_matches_oracle(emu, oracle, fixtures, sr, rm, B):
+    """The CUDA kernel's per-thread code and barrier schedule, executed on CPU threads, vs the oracle:
+    chained state over 5 chunks, ragged tail, random carried-in state and context."""
+    from silero_vad_b200.model import WEIGHTS
+    n, ctx = (512, 64) if sr == 16000 else (256, 32)
+    a = fixtures["test16k"]["audio"]
+    dec = 1 if sr == 16000 else 2
+    x = np.stack([a[(9000 * b)::dec][: n * 5 - 37] for b in range(B)]).copy()
+    st = (np.random.default_rng(1).standard_normal((2, B, 128)) * 0.1).astype(np.float32)
+    cx = (np.random.default_rng(2).standard_normal((B, ctx)) * 0.1).astype(np.float32)
+    st_o, cx_o = st.copy(), cx.copy()
+    want = oracle.audio_forward(x, sr, state=st_o, context=cx_o, nthreads=2)
+    probs = np.zeros_like(want)
+    st_e, cx_e = np.zeros_like(st), np.zeros_like(cx)
+    rc = emu.svad_emu_forward(str(WEIGHTS).encode(), sr, rm, B, x.shape[1], x.ctypes.data, st.ctypes.data, cx.ctypes.data,
+                              st_e.ctypes.data, cx_e.ctypes.data, probs.ctypes.data)
+    assert rc == 0
+    assert np.abs(probs - want).max() < 2e-5
+    assert np.abs(st_e - st_o).max() < 2e-5
+    assert np.array_equal(cx_e, cx_o)
+
+
+def test_validate_input_messages():
+    from silero_vad_b200.model import SileroVADB200
+    import torch
+    m = SileroVADB200.__new__(SileroVADB200)     # host-side validation needs no device
+    m.sample_rates = [8000, 16000]
+    x, sr = m._validate_input(torch.zeros(1024), 32000)
+    assert tuple(x.shape) == (1, 512) and sr == 16000
+    with pytest.raises(ValueError, match="Too many dimensions"):
+        m._validate_input(torch.zeros(1, 1, 512), 16000)
+    with pytest.raises(ValueError, match="Supported sampling rates"):
+        m._validate_input(torch.zeros(512), 22050)
+    with pytest.raises(ValueError, match="too short"):
+        m._validate_input(torch.zeros(100), 16000)
