@@ -77,8 +77,8 @@ class Engine:
         self.device = int(device)
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().svad_engine_destroy(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.svad_engine_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     __del__ = close

@@ -34,6 +34,7 @@ struct GpuEnv {
     __device__ __forceinline__ int tid() const { return tid_; }
     __device__ __forceinline__ float* smem() { return sm; }
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
     __device__ __forceinline__ void issue(long it) {  // one thread
         const int idx = (int)(it % Geo<SR16>::nslab), stage = (int)(it % kStages);
         const uint32_t bytes = (uint32_t)Tape<SR16>::slab_len(idx) * 4u;

@@ -58,7 +58,7 @@ struct Geo {
 // mag  [4][F][32]      (later aliased by e1 [2][64][32], e2 [64][32], e3 [128][32])
 // e0   [4][128][32]    (aliased by the FFT exchange planes Zre/Zim [32][257] during the STFT)
 // h    [128][32]
-// consts: b0[128] b1[64] b2[64] b3[128] bl[512] wout[128] bout[1] pad[3] win[256]
+// consts: b0[128] b1[64] b2[64] b3[128] bl[512] wout[128] bout[1] pad[3] win[256] twr[256] twi[256]
 struct SmemMap {
     static constexpr int mag = 0;
     static constexpr int mag_floats = 4 * 129 * kSlots;          // 16512
@@ -73,7 +73,8 @@ struct SmemMap {
     static constexpr int h = e0 + e0_floats;
     static constexpr int consts = h + kHid * kSlots;
     static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_bout = 1024, c_win = 1028;
-    static constexpr int consts_floats = 1028 + 256;
+    static constexpr int c_twr = c_win + 256, c_twi = c_twr + 256;   // pass-A twiddles W_N^{k1 r} at [k1*16 + r]
+    static constexpr int consts_floats = c_twi + 256;
     static constexpr int headp = consts + consts_floats;         // [32] probabilities of this step
     static constexpr int stage = headp + kSlots;                 // must be 16B aligned (x4 bytes)
     static constexpr int stage_floats = kStageBytes / 4;
@@ -105,8 +106,6 @@ SVAD_HD int slot_to_local(int s) {  // local stream index of a valid slot
 struct Regs {
     float acc[64];   // GEMM accumulators of the current layer
     float c[16];     // LSTM cell state: [row i][unit u] -> c[i*2+u]
-    float twr[16];   // pass-A twiddles W_N^{k1*r}, k1 < NQ
-    float twi[16];
 };
 
 // ---------------------------------------------------------------- small complex FFTs
@@ -200,39 +199,84 @@ SVAD_HD float window_sample(const float* audio, long L, const float* ctx_in, lon
 }
 
 // ---------------------------------------------------------------- STFT pass A
-// Thread (half-warp hw, residue r = tid & 15) transforms the residue-r subsequences of frame f of two
-// slots (sa = warp + 16*half, sb = sa + 8) with one complex NQ-point FFT, applies W_N^{k1 r} and stores
-// Z_r[k1] for k1 < NQ into the exchange planes  Z[slot][k1*16 + r].
+// The STFT runs in 4 rounds; round (hs, fp) covers the 16 slots [16*hs, 16*hs+16) and the frame pair
+// (2*fp, 2*fp+1).  Thread (half-warp hw = tid >> 4, residue r = tid & 15) owns slot 16*hs + hw and
+// transforms the residue-r subsequences of BOTH frames with one complex NQ-point FFT (frame 2fp in the
+// real part, frame 2fp+1 in the imaginary part -- two frames of the SAME stream, so no rounding noise
+// ever crosses between streams), applies W_N^{k1 r} and stores Z_r[k1], k1 < NQ, into the exchange planes
+// Z[item][k1*16 + r] with item = zitem(hw, fr).
+SVAD_HD int zitem(int hw, int fr) { return (hw >> 1) + 8 * fr + 16 * (hw & 1); }   // bank-conflict-free stores
+SVAD_HD int zitem_hw(int item) { return 2 * (item & 7) + (item >> 4); }
+SVAD_HD int zitem_fr(int item) { return (item >> 3) & 1; }
+
+// Raw (unwindowed) samples of one round for this thread: xa[q] = frame 2fp, xb[q] = frame 2fp+1, m = r + 16 q.
+// `fast` (CTA-uniform): the whole padded window of chunk t lies inside the row, so the addresses are affine in
+// (r, q) with the reflection resolved at compile time; otherwise the generic fetch handles context / zero tail.
 template <bool SR16>
-SVAD_HD void stft_pass_a(const Tc& tc, float* sm, const Regs& rg, int f,
-                         const float* audio_a, const float* ctx_a, const float* audio_b, const float* ctx_b,
-                         long L, long t) {
+SVAD_HD void stft_load(int tid, int fp, const float* audio, const float* ctx_in, long L, long t, bool fast,
+                       float (&xa)[Geo<SR16>::NQ], float (&xb)[Geo<SR16>::NQ]) {
+    using G = Geo<SR16>;
+    const int r = tid & 15;
+    if (!audio) {
+#pragma unroll
+        for (int q = 0; q < G::NQ; q++) { xa[q] = 0.0f; xb[q] = 0.0f; }
+        return;
+    }
+    if (fast) {
+        const float* p = audio + t * G::n - G::ctx;   // window origin
+#pragma unroll
+        for (int q = 0; q < G::NQ; q++) {
+            const int m = r + 16 * q;
+            const int ia = G::hop * (2 * fp) + m, ib = G::hop * (2 * fp + 1) + m;   // ia < L1 always
+            // frame 3 runs into the reflect pad for m >= L1 - 3 hop (a multiple of 16, so independent of r)
+            const bool refl = (fp == 1) && (16 * q >= G::L1 - 3 * G::hop);
+            const int jb = refl ? 2 * G::L1 - 2 - ib : ib;
+#if defined(__CUDA_ARCH__)
+            xa[q] = __ldg(p + ia);
+            xb[q] = __ldg(p + jb);
+#else
+            xa[q] = p[ia];
+            xb[q] = p[jb];
+#endif
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < G::NQ; q++) {
+            const int m = r + 16 * q;
+            xa[q] = window_sample<SR16>(audio, L, ctx_in, t, G::hop * (2 * fp) + m);
+            xb[q] = window_sample<SR16>(audio, L, ctx_in, t, G::hop * (2 * fp + 1) + m);
+        }
+    }
+}
+
+template <bool SR16>
+SVAD_HD void stft_pass_a(const Tc& tc, float* sm, const float (&xa)[Geo<SR16>::NQ], const float (&xb)[Geo<SR16>::NQ]) {
     using G = Geo<SR16>;
     constexpr int NQ = G::NQ;
-    const int r = tc.tid & 15, half = (tc.tid >> 4) & 1;
-    const int sa = tc.warp + 16 * half, sb = sa + 8;
-    const float* win = sm + SmemMap::consts + SmemMap::c_win;
+    const int r = tc.tid & 15, hw = tc.tid >> 4;
+    const float* win = sm + SmemMap::consts + SmemMap::c_win + r;
+    const float* twr = sm + SmemMap::consts + SmemMap::c_twr + r;
+    const float* twi = sm + SmemMap::consts + SmemMap::c_twi + r;
     float zr[NQ], zi[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-        int m = r + 16 * q;
-        float w = win[m];  // 0.5 * periodic Hann
-        zr[q] = audio_a ? w * window_sample<SR16>(audio_a, L, ctx_a, t, G::hop * f + m) : 0.0f;
-        zi[q] = audio_b ? w * window_sample<SR16>(audio_b, L, ctx_b, t, G::hop * f + m) : 0.0f;
+        const float w = win[16 * q];  // 0.5 * periodic Hann at m = r + 16 q
+        zr[q] = w * xa[q];
+        zi[q] = w * xb[q];
     }
     fft_dif<NQ>(zr, zi);
-    float* za_re = sm + SmemMap::zre + sa * SmemMap::zpitch + r;
-    float* za_im = sm + SmemMap::zim + sa * SmemMap::zpitch + r;
-    float* zb_re = sm + SmemMap::zre + sb * SmemMap::zpitch + r;
-    float* zb_im = sm + SmemMap::zim + sb * SmemMap::zpitch + r;
+    const int ia = zitem(hw, 0), ib = zitem(hw, 1);
+    float* za_re = sm + SmemMap::zre + ia * SmemMap::zpitch + r;
+    float* za_im = sm + SmemMap::zim + ia * SmemMap::zpitch + r;
+    float* zb_re = sm + SmemMap::zre + ib * SmemMap::zpitch + r;
+    float* zb_im = sm + SmemMap::zim + ib * SmemMap::zpitch + r;
 #pragma unroll
     for (int k = 0; k < NQ; k++) {
-        constexpr int dummy = 0; (void)dummy;
         const int pk = bitrev(k, ilog2(NQ)), pn = bitrev((NQ - k) % NQ, ilog2(NQ));
         // Ya = Z[k] + conj(Z[-k]) ; Yb = -i (Z[k] - conj(Z[-k]))   (the 1/2 lives in the window)
-        float yar = zr[pk] + zr[pn], yai = zi[pk] - zi[pn];
-        float ybr = zi[pk] + zi[pn], ybi = zr[pn] - zr[pk];
-        float wr = rg.twr[k], wi = rg.twi[k];
+        const float yar = zr[pk] + zr[pn], yai = zi[pk] - zi[pn];
+        const float ybr = zi[pk] + zi[pn], ybi = zr[pn] - zr[pk];
+        const float wr = twr[k * 16], wi = twi[k * 16];
         za_re[k * 16] = yar * wr - yai * wi;
         za_im[k * 16] = yar * wi + yai * wr;
         zb_re[k * 16] = ybr * wr - ybi * wi;
@@ -241,18 +285,20 @@ SVAD_HD void stft_pass_a(const Tc& tc, float* sm, const Regs& rg, int f,
 }
 
 // ---------------------------------------------------------------- STFT pass C
-// Thread (lane = slot) takes k1 and runs the 16-point DFT over r; bins k1 + NQ*k2, k2 < 8 (and N/2 for k1 = 0).
+// Thread (lane = exchange item -> slot, frame) takes k1 and runs the 16-point DFT over r;
+// bins k1 + NQ*k2, k2 < 8 (and N/2 for k1 = 0) of that (slot, frame) go to mag[frame][bin][slot].
 template <bool SR16>
-SVAD_HD void stft_pass_c(const Tc& tc, float* sm, int f, int k1) {
+SVAD_HD void stft_pass_c(const Tc& tc, float* sm, int hs, int fp, int k1) {
     using G = Geo<SR16>;
-    const int s = tc.lane;
-    const float* zre = sm + SmemMap::zre + s * SmemMap::zpitch + k1 * 16;
-    const float* zim = sm + SmemMap::zim + s * SmemMap::zpitch + k1 * 16;
+    const int item = tc.lane;
+    const int slot = 16 * hs + zitem_hw(item), f = 2 * fp + zitem_fr(item);
+    const float* zre = sm + SmemMap::zre + item * SmemMap::zpitch + k1 * 16;
+    const float* zim = sm + SmemMap::zim + item * SmemMap::zpitch + k1 * 16;
     float xr[16], xi[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) { xr[r] = zre[r]; xi[r] = zim[r]; }
     fft_dif<16>(xr, xi);
-    float* mg = sm + SmemMap::mag + (f * G::F) * kSlots + s;
+    float* mg = sm + SmemMap::mag + (f * G::F) * kSlots + slot;
 #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) {
         const int p = bitrev(k2, 4);
@@ -265,15 +311,21 @@ SVAD_HD void stft_pass_c(const Tc& tc, float* sm, int f, int k1) {
 }
 
 // ---------------------------------------------------------------- helpers
-SVAD_HD void load8(const float* base, int row0, int row1, float (&x)[8]) {
-    f4 a = *reinterpret_cast<const f4*>(base + row0);
-    f4 b = *reinterpret_cast<const f4*>(base + row1);
+// Activation rows are 32 slots = 8 float4 groups; group g of channel ch is stored at physical group g ^ key(ch)
+// so that the 8 lanes of a warp that write 8 different channels of the same row group hit 8 different bank
+// groups (STS.128 conflict-free) while a reader, for whom ch is warp-uniform, just follows the permutation.
+SVAD_HD int key_hi(int ch) { return (ch >> 1) & 7; }   // e0, e3, h   (writers own channel pairs)
+SVAD_HD int key_lo(int ch) { return ch & 7; }          // e1, e2      (writers own single channels)
+SVAD_HD int swz_slot(int slot, int key) { return (((slot >> 2) ^ key) << 2) | (slot & 3); }
+SVAD_HD void load8(const float* row, int lm, int key, float (&x)[8]) {
+    f4 a = *reinterpret_cast<const f4*>(row + ((lm ^ key) << 2));
+    f4 b = *reinterpret_cast<const f4*>(row + (((4 + lm) ^ key) << 2));
     x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
-SVAD_HD void store8(float* base, int row0, int row1, const float (&x)[8]) {
+SVAD_HD void store8(float* row, int lm, int key, const float (&x)[8]) {
     f4 a{x[0], x[1], x[2], x[3]}, b{x[4], x[5], x[6], x[7]};
-    *reinterpret_cast<f4*>(base + row0) = a;
-    *reinterpret_cast<f4*>(base + row1) = b;
+    *reinterpret_cast<f4*>(row + ((lm ^ key) << 2)) = a;
+    *reinterpret_cast<f4*>(row + (((4 + lm) ^ key) << 2)) = b;
 }
 SVAD_HD float relu(float v) { return v > 0.0f ? v : 0.0f; }   // NaN -> 0 like fmaxf(v, 0)
 SVAD_HD float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -292,13 +344,13 @@ SVAD_HD void enc0_init(const Tc& tc, const float* sm, Regs& rg) {
 template <bool SR16, int RM>
 SVAD_HD void enc0_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int c0, int c1) {
     using G = Geo<SR16>;
-    const int oc = 16 * tc.warp + 2 * tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const int oc = 16 * tc.warp + 2 * tc.ln;
     const float* mag = sm + SmemMap::mag;
 #pragma unroll 1
     for (int c = c0; c < c1; c++) {
         float x[4][8];
 #pragma unroll
-        for (int f = 0; f < 4; f++) load8(mag + (f * G::F + c) * kSlots, r0, r1, x[f]);
+        for (int f = 0; f < 4; f++) load8(mag + (f * G::F + c) * kSlots, tc.lm, 0, x[f]);
         const float* wp = slab + (c - c0) * 384 + oc;
         f2 w[3];
 #pragma unroll
@@ -319,7 +371,7 @@ SVAD_HD void enc0_slab(const Tc& tc, const float* sm, const float* slab, Regs& r
 }
 template <bool SR16, int RM>
 SVAD_HD void enc0_store(const Tc& tc, float* sm, const Regs& rg) {
-    const int oc = 16 * tc.warp + 2 * tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const int oc = 16 * tc.warp + 2 * tc.ln;
 #pragma unroll
     for (int t = 0; t < 4; t++)
 #pragma unroll
@@ -327,7 +379,7 @@ SVAD_HD void enc0_store(const Tc& tc, float* sm, const Regs& rg) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(rg.acc[(t * 8 + i) * 2 + u]) : 0.0f;
-            store8(sm + SmemMap::e0 + (t * 128 + oc + u) * kSlots, r0, r1, v);
+            store8(sm + SmemMap::e0 + (t * 128 + oc + u) * kSlots, tc.lm, key_hi(oc), v);
         }
 }
 
@@ -342,13 +394,13 @@ SVAD_HD void enc1_init(const Tc& tc, const float* sm, Regs& rg) {
 }
 template <int RM>
 SVAD_HD void enc1_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int c0, int c1) {
-    const int o = 8 * tc.warp + tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const int o = 8 * tc.warp + tc.ln;
     const float* e0 = sm + SmemMap::e0;
 #pragma unroll 2
     for (int c = c0; c < c1; c++) {
         float x[4][8];
 #pragma unroll
-        for (int f = 0; f < 4; f++) load8(e0 + (f * 128 + c) * kSlots, r0, r1, x[f]);
+        for (int f = 0; f < 4; f++) load8(e0 + (f * 128 + c) * kSlots, tc.lm, key_hi(c), x[f]);
         const float* wp = slab + (c - c0) * 192 + o;
         const float w0 = wp[0], w1 = wp[64], w2 = wp[128];
 #pragma unroll
@@ -369,7 +421,7 @@ SVAD_HD void enc1_store(const Tc& tc, float* sm, const Regs& rg) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(rg.acc[t * 8 + i]) : 0.0f;
-        store8(sm + SmemMap::e1 + (t * 64 + o) * kSlots, tc.row0(), tc.row1(), v);
+        store8(sm + SmemMap::e1 + (t * 64 + o) * kSlots, tc.lm, key_lo(o), v);
     }
 }
 
@@ -377,7 +429,7 @@ SVAD_HD void enc1_store(const Tc& tc, float* sm, const Regs& rg) {
 // slab = W2p[c][jj][64], jj=0 <-> tap 1 (frame 0), jj=1 <-> tap 2 (frame 1); one slab, 64 channels.
 template <int RM>
 SVAD_HD void enc2_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
-    const int o = 8 * tc.warp + tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const int o = 8 * tc.warp + tc.ln;
     float b = sm[SmemMap::consts + SmemMap::c_b2 + o];
     float acc[8];
 #pragma unroll
@@ -385,8 +437,8 @@ SVAD_HD void enc2_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
 #pragma unroll 4
     for (int c = 0; c < 64; c++) {
         float x0[8], x1[8];
-        load8(sm + SmemMap::e1 + c * kSlots, r0, r1, x0);
-        load8(sm + SmemMap::e1 + (64 + c) * kSlots, r0, r1, x1);
+        load8(sm + SmemMap::e1 + c * kSlots, tc.lm, key_lo(c), x0);
+        load8(sm + SmemMap::e1 + (64 + c) * kSlots, tc.lm, key_lo(c), x1);
         const float w0 = slab[c * 128 + o], w1 = slab[c * 128 + 64 + o];
 #pragma unroll
         for (int i = 0; i < RM; i++) { acc[i] = fmaf(w0, x0[i], acc[i]); acc[i] = fmaf(w1, x1[i], acc[i]); }
@@ -394,7 +446,7 @@ SVAD_HD void enc2_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(acc[i]) : 0.0f;
-    store8(sm + SmemMap::e2 + o * kSlots, r0, r1, v);
+    store8(sm + SmemMap::e2 + o * kSlots, tc.lm, key_lo(o), v);
     (void)rg;
 }
 
@@ -402,7 +454,7 @@ SVAD_HD void enc2_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
 // slab = W3p[c][128]; cols 16*warp + 2*ln + u.
 template <int RM>
 SVAD_HD void enc3_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
-    const int oc = 16 * tc.warp + 2 * tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const int oc = 16 * tc.warp + 2 * tc.ln;
     const float* b3 = sm + SmemMap::consts + SmemMap::c_b3 + oc;
     float acc[8][2];
 #pragma unroll
@@ -410,7 +462,7 @@ SVAD_HD void enc3_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
 #pragma unroll 4
     for (int c = 0; c < 64; c++) {
         float x[8];
-        load8(sm + SmemMap::e2 + c * kSlots, r0, r1, x);
+        load8(sm + SmemMap::e2 + c * kSlots, tc.lm, key_lo(c), x);
         f2 w = *reinterpret_cast<const f2*>(slab + c * 128 + oc);
 #pragma unroll
         for (int i = 0; i < RM; i++) { acc[i][0] = fmaf(w.x, x[i], acc[i][0]); acc[i][1] = fmaf(w.y, x[i], acc[i][1]); }
@@ -420,7 +472,7 @@ SVAD_HD void enc3_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(acc[i][u]) : 0.0f;
-        store8(sm + SmemMap::e3 + (oc + u) * kSlots, r0, r1, v);
+        store8(sm + SmemMap::e3 + (oc + u) * kSlots, tc.lm, key_hi(oc), v);
     }
     (void)rg;
 }
@@ -440,12 +492,12 @@ SVAD_HD void lstm_init(const Tc& tc, const float* sm, Regs& rg) {
 }
 template <int RM>
 SVAD_HD void lstm_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int k0) {
-    const int nc = 64 * tc.warp + 4 * tc.ln, r0 = tc.row0(), r1 = tc.row1();
+    const int nc = 64 * tc.warp + 4 * tc.ln;
     const float* a = (k0 < kHid) ? sm + SmemMap::e3 + k0 * kSlots : sm + SmemMap::h + (k0 - kHid) * kSlots;
 #pragma unroll 4
     for (int kk = 0; kk < 16; kk++) {
         float x[8];
-        load8(a + kk * kSlots, r0, r1, x);
+        load8(a + kk * kSlots, tc.lm, key_hi(kk), x);
         f4 w0 = *reinterpret_cast<const f4*>(slab + kk * kGates + nc);
         f4 w1 = *reinterpret_cast<const f4*>(slab + kk * kGates + nc + 32);
         const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -474,22 +526,21 @@ SVAD_HD void lstm_epilogue(const Tc& tc, float* sm, Regs& rg) {
                 hv[i] = 0.0f;
             }
         }
-        store8(sm + SmemMap::h + (j0 + u) * kSlots, tc.row0(), tc.row1(), hv);
+        store8(sm + SmemMap::h + (j0 + u) * kSlots, tc.lm, key_hi(j0), hv);
     }
 }
 // head: thread tid < 32 (slot = tid): p = sigmoid(sum_j wout[j] relu(h'[j]) + bout)
 SVAD_HD float head_prob(const float* sm, int slot) {
     const float* wout = sm + SmemMap::consts + SmemMap::c_wout;
-    const float* h = sm + SmemMap::h + slot;
-    float a0 = sm[SmemMap::consts + SmemMap::c_bout], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* h = sm + SmemMap::h;
+    float a0 = sm[SmemMap::consts + SmemMap::c_bout], a1 = 0.f;
 #pragma unroll 8
-    for (int j = 0; j < kHid; j += 4) {
-        a0 = fmaf(wout[j], relu(h[j * kSlots]), a0);
-        a1 = fmaf(wout[j + 1], relu(h[(j + 1) * kSlots]), a1);
-        a2 = fmaf(wout[j + 2], relu(h[(j + 2) * kSlots]), a2);
-        a3 = fmaf(wout[j + 3], relu(h[(j + 3) * kSlots]), a3);
+    for (int j = 0; j < kHid; j += 2) {   // units j, j+1 share a swizzle key
+        const int ps = swz_slot(slot, key_hi(j));
+        a0 = fmaf(wout[j], relu(h[j * kSlots + ps]), a0);
+        a1 = fmaf(wout[j + 1], relu(h[(j + 1) * kSlots + ps]), a1);
     }
-    return sigmoid_acc((a0 + a1) + (a2 + a3));
+    return sigmoid_acc(a0 + a1);
 }
 
 }  // namespace svad

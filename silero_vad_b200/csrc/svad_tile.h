@@ -37,23 +37,21 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
     Regs rg;
     constexpr int BT = 4 * RM;
 
-    // constants -> smem, pass-A twiddles -> registers
-    for (int i = tc.tid; i < SmemMap::consts_floats; i += kThreads) sm[SmemMap::consts + i] = a.consts[i];
+    // constants -> smem; pass-A twiddle table W_N^{k1 r} (k1 < NQ, r < 16) computed in place
+    for (int i = tc.tid; i < SmemMap::c_twr; i += kThreads) sm[SmemMap::consts + i] = a.consts[i];
     {
-        const int r = tc.tid & 15;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (k < G::NQ) {
-                float s, c;
-                const float x = -2.0f * (float)((k * r) % G::N) / (float)G::N;  // angle / pi
+        const int k = tc.tid >> 4, r = tc.tid & 15;
+        float s = 0.0f, c = 1.0f;
+        if (k < G::NQ) {
+            const float x = -2.0f * (float)((k * r) % G::N) / (float)G::N;  // angle / pi
 #if defined(__CUDA_ARCH__)
-                sincospif(x, &s, &c);
+            sincospif(x, &s, &c);
 #else
-                s = (float)sin(M_PI * (double)x); c = (float)cos(M_PI * (double)x);
+            s = (float)sin(M_PI * (double)x); c = (float)cos(M_PI * (double)x);
 #endif
-                rg.twr[k] = c; rg.twi[k] = s;
-            } else { rg.twr[k] = 1.0f; rg.twi[k] = 0.0f; }
         }
+        sm[SmemMap::consts + SmemMap::c_twr + tc.tid] = c;
+        sm[SmemMap::consts + SmemMap::c_twi + tc.tid] = s;
     }
     int my_tiles = 0;
     for (int tile = first_tile; tile < ntiles; tile += tile_stride) my_tiles++;
@@ -69,7 +67,7 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
             const int g = g0 + slot_to_local<RM>(s);
             float v = 0.0f;
             if (a.state_in && slot_valid<RM>(s) && g < a.B) v = a.state_in[(long)g * kHid + j];
-            sm[SmemMap::h + i] = v;
+            sm[SmemMap::h + j * kSlots + swz_slot(s, key_hi(j))] = v;
         }
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -82,26 +80,47 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                 if (a.state_in && i < RM && g < a.B) v = a.state_in[((long)a.B + g) * kHid + j];
                 rg.c[i * 2 + u] = v;
             }
-        // audio rows of the two slots this thread feeds in STFT pass A
-        const int half = (tc.tid >> 4) & 1;
-        const int sa = tc.warp + 16 * half, sb = sa + 8;
-        const int ga = g0 + slot_to_local<RM>(sa), gb = g0 + slot_to_local<RM>(sb);
-        const bool va = slot_valid<RM>(sa) && ga < a.B, vb = slot_valid<RM>(sb) && gb < a.B;
-        const float* aud_a = va ? a.audio + (long)ga * a.ld : nullptr;
-        const float* aud_b = vb ? a.audio + (long)gb * a.ld : nullptr;
-        const float* cx_a = (va && a.ctx_in) ? a.ctx_in + (long)ga * a.ctx_ld : nullptr;
-        const float* cx_b = (vb && a.ctx_in) ? a.ctx_in + (long)gb * a.ctx_ld : nullptr;
+        // audio rows of the two slots (one per 16-slot half) this thread feeds in STFT pass A
+        const float* aud[2];
+        const float* cxp[2];
+#pragma unroll
+        for (int hs = 0; hs < 2; hs++) {
+            const int sl = 16 * hs + (tc.tid >> 4);
+            const int gs = g0 + slot_to_local<RM>(sl);
+            const bool v = slot_valid<RM>(sl) && gs < a.B;
+            aud[hs] = v ? a.audio + (long)gs * a.ld : nullptr;
+            cxp[hs] = (v && a.ctx_in) ? a.ctx_in + (long)gs * a.ctx_ld : nullptr;
+        }
         env.sync();
 
+        float xa[G::NQ], xb[G::NQ];   // raw samples of the STFT round about to be transformed
         for (long t = 0; t < a.T; t++) {
-            // ---------------- STFT
+            // ---------------- STFT: 4 rounds (slot half hs, frame pair fp); the raw samples of round i+1 are
+            // fetched into registers while round i is transformed, round 0 of the next step at the end of this one.
+            const bool fast = (t > 0) && ((t + 1) * G::n <= a.L);
+            if (t + 1 < a.T) {   // pull the next chunk of every stream of the tile into L2
+#pragma unroll
+                for (int i = tc.tid; i < BT * (G::n / 32); i += kThreads) {
+                    const int loc = i / (G::n / 32), line = i % (G::n / 32), g = g0 + loc;
+                    const long off = (t + 1) * G::n + line * 32;
+                    if (g < a.B && off < a.L) env.prefetch_l2(a.audio + (long)g * a.ld + off);
+                }
+            }
+            if (t == 0) stft_load<SR16>(tc.tid, 0, aud[0], cxp[0], a.L, t, fast, xa, xb);
 #pragma unroll 1
-            for (int f = 0; f < 4; f++) {
-                stft_pass_a<SR16>(tc, sm, rg, f, aud_a, cx_a, aud_b, cx_b, a.L, t);
+            for (int rnd = 0; rnd < 4; rnd++) {
+                const int hs = rnd >> 1, fp = rnd & 1;
+                float na[G::NQ], nb[G::NQ];
+                if (rnd < 3) stft_load<SR16>(tc.tid, (rnd + 1) & 1, rnd >= 1 ? aud[1] : aud[0], rnd >= 1 ? cxp[1] : cxp[0], a.L, t, fast, na, nb);
+                stft_pass_a<SR16>(tc, sm, xa, xb);
                 env.sync();
 #pragma unroll
-                for (int kk = 0; kk < G::NQ / 8; kk++) stft_pass_c<SR16>(tc, sm, f, tc.warp * (G::NQ / 8) + kk);
+                for (int kk = 0; kk < G::NQ / 8; kk++) stft_pass_c<SR16>(tc, sm, hs, fp, tc.warp * (G::NQ / 8) + kk);
                 env.sync();
+                if (rnd < 3) {
+#pragma unroll
+                    for (int q = 0; q < G::NQ; q++) { xa[q] = na[q]; xb[q] = nb[q]; }
+                }
             }
             // ---------------- enc0
             enc0_init<SR16, RM>(tc, sm, rg);
@@ -151,6 +170,8 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                 const int g = g0 + slot_to_local<RM>(tc.tid);
                 if (slot_valid<RM>(tc.tid) && g < a.B) a.probs[(long)g * a.ldp + t] = head_prob(sm, tc.tid);
             }
+            if (t + 1 < a.T)
+                stft_load<SR16>(tc.tid, 0, aud[0], cxp[0], a.L, t + 1, ((t + 2) * G::n <= a.L), xa, xb);
         }
         // ---- tile exit: carry state / context out
         env.sync();
@@ -158,7 +179,7 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
             for (int i = tc.tid; i < kHid * kSlots; i += kThreads) {
                 const int s = i & 31, j = i >> 5;
                 const int g = g0 + slot_to_local<RM>(s);
-                if (slot_valid<RM>(s) && g < a.B) a.state_out[(long)g * kHid + j] = sm[SmemMap::h + i];
+                if (slot_valid<RM>(s) && g < a.B) a.state_out[(long)g * kHid + j] = sm[SmemMap::h + j * kSlots + swz_slot(s, key_hi(j))];
             }
 #pragma unroll
             for (int i = 0; i < 8; i++)

@@ -27,6 +27,7 @@ struct EmuEnv {
     int tid() const { return tid_; }
     float* smem() { return sh->smem.data(); }
     void sync() { pthread_barrier_wait(&sh->bar); }
+    void prefetch_l2(const float*) {}
     void issue(long it) {
         const int idx = (int)(it % Geo<SR16>::nslab), stage = (int)(it % kStages);
         memcpy(sh->smem.data() + SmemMap::stage + stage * SmemMap::stage_floats, sh->tape + Tape<SR16>::slab_off(idx),
