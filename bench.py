@@ -227,7 +227,20 @@ def run_b200(args):
             dt = float(t.item())
         assert torch.equal(ph, probs.cpu()), "host entry point disagrees with device entry point"
         e2e = {"value": chunks_per_step * esteps / dt, "unit": "chunks/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * T * 4,
-               "ms_per_step": dt / esteps * 1e3}
+               "ms_per_step": dt / esteps * 1e3,
+               "api": "svad_forward_host (C ABI): fp32 host audio in pinned memory, time-sliced H2D overlapped with the kernel, D2H of probabilities"}
+        # same call with int16 PCM host audio (what WAV files hold): half the PCIe bytes, bit-identical probabilities
+        xi = (xh * 32768.0).round().clamp(-32768, 32767).to(torch.int16).pin_memory()
+        pi = torch.empty(B, T).pin_memory()
+        for _ in range(2):
+            eng.forward_host_pcm16(sr, B, L, L, xi.data_ptr(), 0, 0, 0, 0, pi.data_ptr(), T)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            eng.forward_host_pcm16(sr, B, L, L, xi.data_ptr(), 0, 0, 0, 0, pi.data_ptr(), T)
+        barrier()
+        dti = time.perf_counter() - t0
+        e2e["pcm16"] = {"value": B * T * world * esteps / dti, "unit": "chunks/s", "h2d_bytes_per_step": B * L * 2, "ms_per_step": dti / esteps * 1e3}
 
     if rank != 0:
         if world > 1:

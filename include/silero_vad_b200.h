@@ -63,6 +63,12 @@ int svad_forward_device(svad_engine* e, int sr, int B, int64_t L, int64_t ld, co
                         const float* d_state_in, const float* d_ctx_in, float* d_state_out, float* d_ctx_out,
                         float* d_probs, int64_t ldp, void* stream);
 
+/* Same, with int16 PCM samples (scaled by 2^-15 on load = the int16/32768 convention of examples/cpp/wav.h:95-136
+ * and examples/onnx_sequence/run.py:115-119): half the HBM / PCIe bytes per chunk, bit-identical probabilities. */
+int svad_forward_device_pcm16(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const int16_t* d_audio,
+                              const float* d_state_in, const float* d_ctx_in, float* d_state_out, float* d_ctx_out,
+                              float* d_probs, int64_t ldp, void* stream);
+
 /* One chunk, the stateless ONNX contract (utils_vad.py:80-82; examples/cpp/silero-vad-onnx.cpp:176-195):
  *   d_input f32[B][ctx+n] (context already prepended), d_state_in f32[2][B][128] (NULL = zeros)
  *   -> d_prob f32[B], d_state_out f32[2][B][128] (may alias d_state_in). */
@@ -73,6 +79,8 @@ int svad_step_device(svad_engine* e, int sr, int B, const float* d_input, const 
  * (pinned staging inside the engine).  These are what bench.py's `e2e` times. */
 int svad_forward_host(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const float* audio, const float* state_in,
                       const float* ctx_in, float* state_out, float* ctx_out, float* probs, int64_t ldp);
+int svad_forward_host_pcm16(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const int16_t* audio, const float* state_in,
+                            const float* ctx_in, float* state_out, float* ctx_out, float* probs, int64_t ldp);
 int svad_step_host(svad_engine* e, int sr, int B, const float* input, const float* state_in, float* prob,
                    float* state_out);
 

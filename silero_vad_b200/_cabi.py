@@ -12,7 +12,8 @@ _lib = None
 
 EXPORTS = ["svad_abi_version", "svad_last_error", "svad_engine_create", "svad_engine_destroy",
            "svad_engine_set_tile_rows", "svad_engine_sm_count", "svad_engine_launch_count",
-           "svad_forward_device", "svad_step_device", "svad_forward_host", "svad_step_host",
+           "svad_forward_device", "svad_forward_device_pcm16", "svad_step_device", "svad_forward_host",
+           "svad_forward_host_pcm16", "svad_step_host",
            "svad_segment_params_default", "svad_speech_segments"]
 
 
@@ -48,6 +49,8 @@ def lib():
     L.svad_engine_launch_count.argtypes = [vp]
     L.svad_engine_launch_count.restype = i64
     L.svad_forward_device.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.svad_forward_device_pcm16.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.svad_forward_host_pcm16.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64]
     L.svad_step_device.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.svad_forward_host.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64]
     L.svad_step_host.argtypes = [vp, i32, i32, vp, vp, vp, vp]
@@ -96,6 +99,12 @@ class Engine:
 
     def forward_device(self, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream=0):
         check(lib().svad_forward_device(self._h, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream))
+
+    def forward_device_pcm16(self, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream=0):
+        check(lib().svad_forward_device_pcm16(self._h, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream))
+
+    def forward_host_pcm16(self, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp):
+        check(lib().svad_forward_host_pcm16(self._h, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp))
 
     def step_device(self, sr, B, x1, state_in, prob, state_out, stream=0):
         check(lib().svad_step_device(self._h, sr, B, x1, state_in, prob, state_out, stream))

@@ -34,7 +34,7 @@ struct GpuEnv {
     __device__ __forceinline__ int tid() const { return tid_; }
     __device__ __forceinline__ float* smem() { return sm; }
     __device__ __forceinline__ void sync() { __syncthreads(); }
-    __device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+    __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
     __device__ __forceinline__ void issue(long it) {  // one thread
         const int idx = (int)(it % Geo<SR16>::nslab), stage = (int)(it % kStages);
         const uint32_t bytes = (uint32_t)Tape<SR16>::slab_len(idx) * 4u;
@@ -70,7 +70,7 @@ struct GpuEnv {
 
 constexpr size_t kSmemBytes = (size_t)SmemMap::total_floats * 4 + 64;
 
-template <bool SR16, int RM>
+template <bool SR16, int RM, typename S>
 __global__ void __launch_bounds__(kThreads, 1) svad_fused_fp32(TileArgs a, int ntiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw);
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) svad_fused_fp32(TileArgs a, int n
         for (long i = 0; i < kStages && i < total; i++) env.issue(i);
     }
     __syncthreads();
-    run_cta<SR16, RM>(env, a, (int)blockIdx.x, (int)gridDim.x, ntiles);
+    run_cta<SR16, RM, S>(env, a, (int)blockIdx.x, (int)gridDim.x, ntiles);
 }
 
 }  // namespace
@@ -115,10 +115,12 @@ struct svad_engine {
     float* d_consts[2] = {nullptr, nullptr};
     int64_t launches = 0;
     // staging for the host-buffer entry points
-    float *h_pin = nullptr, *d_buf = nullptr;
-    size_t pin_floats = 0, dbuf_floats = 0;
-    cudaStream_t stream = nullptr;
+    void *h_pin = nullptr, *d_buf = nullptr;
+    size_t pin_bytes = 0, dbuf_bytes = 0;
+    cudaStream_t stream = nullptr, stream_copy = nullptr;
+    cudaEvent_t ev[8] = {};
 };
+constexpr int kMaxSlices = 8;
 
 extern "C" int svad_abi_version(void) { return 1; }
 extern "C" const char* svad_last_error(void) { return g_err.c_str(); }
@@ -151,6 +153,8 @@ extern "C" int svad_engine_create(const char* weights_path, int device, svad_eng
         CUDA_TRY(cudaMemcpy(e->d_consts[b], pb[b].consts.data(), pb[b].consts.size() * 4, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxSlices; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
     *out = e;
     return SVAD_OK;
 }
@@ -162,6 +166,8 @@ extern "C" void svad_engine_destroy(svad_engine* e) {
     if (e->h_pin) cudaFreeHost(e->h_pin);
     if (e->d_buf) cudaFree(e->d_buf);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream_copy) cudaStreamDestroy(e->stream_copy);
+    for (int i = 0; i < kMaxSlices; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     delete e;
 }
 
@@ -173,9 +179,9 @@ extern "C" int svad_engine_set_tile_rows(svad_engine* e, int rows) {
 extern "C" int svad_engine_sm_count(const svad_engine* e) { return e ? e->sms : 0; }
 extern "C" int64_t svad_engine_launch_count(const svad_engine* e) { return e ? e->launches : 0; }
 
-template <bool SR16, int RM>
+template <bool SR16, int RM, typename S>
 static int launch(svad_engine* e, const TileArgs& a, cudaStream_t st) {
-    auto kern = svad_fused_fp32<SR16, RM>;
+    auto kern = svad_fused_fp32<SR16, RM, S>;
     static bool configured[16] = {};  // per device
     if (!configured[e->device & 15]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -203,18 +209,21 @@ static int pick_rows(const svad_engine* e, int B) {
     return best;
 }
 
-template <bool SR16>
+template <bool SR16, typename S>
 static int launch_rm(svad_engine* e, const TileArgs& a, cudaStream_t st) {
     switch (pick_rows(e, a.B)) {
-        case 4: return launch<SR16, 4>(e, a, st);
-        case 5: return launch<SR16, 5>(e, a, st);
-        case 6: return launch<SR16, 6>(e, a, st);
-        case 7: return launch<SR16, 7>(e, a, st);
-        default: return launch<SR16, 8>(e, a, st);
+        case 4: return launch<SR16, 4, S>(e, a, st);
+        case 5: return launch<SR16, 5, S>(e, a, st);
+        case 6: return launch<SR16, 6, S>(e, a, st);
+        case 7: return launch<SR16, 7, S>(e, a, st);
+        default: return launch<SR16, 8, S>(e, a, st);
     }
 }
 
-static int forward_impl(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const float* d_audio, const float* d_state_in,
+enum SampleFmt { kF32 = 0, kI16 = 1 };
+static size_t fmt_size(int fmt) { return fmt == kI16 ? 2 : 4; }
+
+static int forward_impl(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const void* d_audio, int fmt, const float* d_state_in,
                         const float* d_ctx_in, int64_t ctx_ld, float* d_state_out, float* d_ctx_out, float* d_probs,
                         int64_t ldp, cudaStream_t st) {
     if (!e) return fail(SVAD_EINVAL, "null engine");
@@ -231,14 +240,22 @@ static int forward_impl(svad_engine* e, int sr, int B, int64_t L, int64_t ld, co
     a.state_in = d_state_in; a.ctx_in = d_ctx_in; a.ctx_ld = ctx_ld;
     a.state_out = d_state_out; a.ctx_out = d_ctx_out;
     a.probs = d_probs; a.ldp = ldp; a.tape = e->d_tape[br]; a.consts = e->d_consts[br];
-    return sr == 16000 ? launch_rm<true>(e, a, st) : launch_rm<false>(e, a, st);
+    if (fmt == kI16) return sr == 16000 ? launch_rm<true, int16_t>(e, a, st) : launch_rm<false, int16_t>(e, a, st);
+    return sr == 16000 ? launch_rm<true, float>(e, a, st) : launch_rm<false, float>(e, a, st);
 }
 
 extern "C" int svad_forward_device(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const float* d_audio,
                                    const float* d_state_in, const float* d_ctx_in, float* d_state_out, float* d_ctx_out,
                                    float* d_probs, int64_t ldp, void* stream) {
-    return forward_impl(e, sr, B, L, ld, d_audio, d_state_in, d_ctx_in, sr == 16000 ? 64 : 32, d_state_out, d_ctx_out, d_probs,
-                        ldp, (cudaStream_t)stream);
+    return forward_impl(e, sr, B, L, ld, d_audio, kF32, d_state_in, d_ctx_in, sr == 16000 ? 64 : 32, d_state_out, d_ctx_out,
+                        d_probs, ldp, (cudaStream_t)stream);
+}
+
+extern "C" int svad_forward_device_pcm16(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const int16_t* d_audio,
+                                         const float* d_state_in, const float* d_ctx_in, float* d_state_out, float* d_ctx_out,
+                                         float* d_probs, int64_t ldp, void* stream) {
+    return forward_impl(e, sr, B, L, ld, d_audio, kI16, d_state_in, d_ctx_in, sr == 16000 ? 64 : 32, d_state_out, d_ctx_out,
+                        d_probs, ldp, (cudaStream_t)stream);
 }
 
 extern "C" int svad_step_device(svad_engine* e, int sr, int B, const float* d_input, const float* d_state_in, float* d_prob,
@@ -247,36 +264,39 @@ extern "C" int svad_step_device(svad_engine* e, int sr, int B, const float* d_in
     const int n = sr == 16000 ? 512 : 256, ctx = n / 8;
     if (B > 0 && (!d_input || !d_prob)) return fail(SVAD_EINVAL, "null input/prob");
     // input rows are [context | chunk]: the chunk is the "audio", the context the carried-in samples
-    return forward_impl(e, sr, B, n, ctx + n, d_input + ctx, d_state_in, d_input, ctx + n, d_state_out, nullptr, d_prob, 1,
+    return forward_impl(e, sr, B, n, ctx + n, d_input + ctx, kF32, d_state_in, d_input, ctx + n, d_state_out, nullptr, d_prob, 1,
                         (cudaStream_t)stream);
 }
 
 // ---- host-buffer twins -------------------------------------------------------------------------
 // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are DMA'd directly;
-// pageable ones are staged through the engine's pinned buffer first.
+// pageable ones are staged through the engine's pinned buffer first.  The audio goes over in time slices
+// (all streams x a few chunks) on a copy stream while the previous slice is being computed with the LSTM
+// state and audio context carried on the device, so PCIe and the SMs overlap.
 static bool is_pinned(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost;
 }
-static int ensure_staging(svad_engine* e, size_t floats) {
-    if (floats > e->pin_floats) {
+
+static int ensure_staging(svad_engine* e, size_t pin_bytes, size_t dev_bytes) {
+    if (pin_bytes > e->pin_bytes) {
         if (e->h_pin) cudaFreeHost(e->h_pin);
-        e->h_pin = nullptr; e->pin_floats = 0;
-        CUDA_TRY(cudaMallocHost(&e->h_pin, floats * 4));
-        e->pin_floats = floats;
+        e->h_pin = nullptr; e->pin_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&e->h_pin, pin_bytes));
+        e->pin_bytes = pin_bytes;
     }
-    if (floats > e->dbuf_floats) {
+    if (dev_bytes > e->dbuf_bytes) {
         if (e->d_buf) cudaFree(e->d_buf);
-        e->d_buf = nullptr; e->dbuf_floats = 0;
-        CUDA_TRY(cudaMalloc(&e->d_buf, floats * 4));
-        e->dbuf_floats = floats;
+        e->d_buf = nullptr; e->dbuf_bytes = 0;
+        CUDA_TRY(cudaMalloc(&e->d_buf, dev_bytes));
+        e->dbuf_bytes = dev_bytes;
     }
     return SVAD_OK;
 }
 
-extern "C" int svad_forward_host(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const float* audio, const float* state_in,
-                                 const float* ctx_in, float* state_out, float* ctx_out, float* probs, int64_t ldp) {
+static int forward_host_impl(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const void* audio, int fmt, const float* state_in,
+                             const float* ctx_in, float* state_out, float* ctx_out, float* probs, int64_t ldp) {
     if (!e) return fail(SVAD_EINVAL, "null engine");
     if (sr != 16000 && sr != 8000) return fail(SVAD_EINVAL, "Supported sampling rates: [8000, 16000] (got %d)", sr);
     if (B < 0 || L < 0 || ld < L) return fail(SVAD_EINVAL, "bad size");
@@ -285,35 +305,71 @@ extern "C" int svad_forward_host(svad_engine* e, int sr, int B, int64_t L, int64
     const int64_t T = (L + n - 1) / n;
     if (T > 0 && (!audio || !probs || ldp < T)) return fail(SVAD_EINVAL, "bad audio/probs");
     CUDA_TRY(cudaSetDevice(e->device));
-    // device layout: audio [B][L] | state [2][B][128] | ctx [B][ctx] | probs [B][T]   (each 16-float aligned)
-    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t o_audio = 0, o_state = al((size_t)B * L), o_ctx = o_state + al((size_t)2 * B * 128),
-                 o_probs = o_ctx + al((size_t)B * ctx), total = o_probs + al((size_t)B * T);
-    int rc = ensure_staging(e, total);
-    if (rc) return rc;
-    float *hp = e->h_pin, *dp = e->d_buf;
-    const bool audio_direct = T > 0 && ld == L && is_pinned(audio);
+    const size_t es = fmt_size(fmt);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    // device: audio [B][L] | state [2][B][128] | ctx [B][ctx] | probs [B][T]      pinned host: same map
+    const size_t o_audio = 0, o_state = al((size_t)B * L * es), o_ctx = o_state + al((size_t)2 * B * 128 * 4),
+                 o_probs = o_ctx + al((size_t)B * ctx * 4), total = o_probs + al((size_t)B * T * 4);
+    const bool audio_direct = T > 0 && is_pinned(audio);
     const bool probs_direct = T > 0 && ldp == T && is_pinned(probs);
-    if (!audio_direct && T > 0)
-        for (int b = 0; b < B; b++) memcpy(hp + o_audio + (size_t)b * L, audio + (size_t)b * ld, (size_t)L * 4);
-    if (state_in) memcpy(hp + o_state, state_in, (size_t)2 * B * 128 * 4);
-    if (ctx_in) memcpy(hp + o_ctx, ctx_in, (size_t)B * ctx * 4);
-    cudaStream_t st = e->stream;
-    if (T > 0)
-        CUDA_TRY(cudaMemcpyAsync(dp + o_audio, audio_direct ? audio : hp + o_audio, (size_t)B * L * 4, cudaMemcpyHostToDevice, st));
-    if (state_in) CUDA_TRY(cudaMemcpyAsync(dp + o_state, hp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyHostToDevice, st));
-    if (ctx_in) CUDA_TRY(cudaMemcpyAsync(dp + o_ctx, hp + o_ctx, (size_t)B * ctx * 4, cudaMemcpyHostToDevice, st));
-    rc = forward_impl(e, sr, B, L, L, dp + o_audio, state_in ? dp + o_state : nullptr, ctx_in ? dp + o_ctx : nullptr, ctx,
-                      state_out ? dp + o_state : nullptr, ctx_out ? dp + o_ctx : nullptr, dp + o_probs, T, st);
+    int rc = ensure_staging(e, total, total);
     if (rc) return rc;
-    if (T > 0) CUDA_TRY(cudaMemcpyAsync(probs_direct ? probs : hp + o_probs, dp + o_probs, (size_t)B * T * 4, cudaMemcpyDeviceToHost, st));
-    if (state_out) CUDA_TRY(cudaMemcpyAsync(hp + o_state, dp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyDeviceToHost, st));
-    if (ctx_out) CUDA_TRY(cudaMemcpyAsync(hp + o_ctx, dp + o_ctx, (size_t)B * ctx * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    for (int b = 0; b < B && T > 0 && !probs_direct; b++) memcpy(probs + (size_t)b * ldp, hp + o_probs + (size_t)b * T, (size_t)T * 4);
+    char *hp = (char*)e->h_pin, *dp = (char*)e->d_buf;
+    float *d_state = (float*)(dp + o_state), *d_ctx = (float*)(dp + o_ctx), *d_probs = (float*)(dp + o_probs);
+    cudaStream_t sc = e->stream_copy, sk = e->stream;
+    // small inputs first (compute stream)
+    if (state_in) {
+        memcpy(hp + o_state, state_in, (size_t)2 * B * 128 * 4);
+        CUDA_TRY(cudaMemcpyAsync(d_state, hp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyHostToDevice, sk));
+    } else {
+        CUDA_TRY(cudaMemsetAsync(d_state, 0, (size_t)2 * B * 128 * 4, sk));
+    }
+    if (ctx_in) {
+        memcpy(hp + o_ctx, ctx_in, (size_t)B * ctx * 4);
+        CUDA_TRY(cudaMemcpyAsync(d_ctx, hp + o_ctx, (size_t)B * ctx * 4, cudaMemcpyHostToDevice, sk));
+    } else {
+        CUDA_TRY(cudaMemsetAsync(d_ctx, 0, (size_t)B * ctx * 4, sk));
+    }
+    // time slices: at least 4 chunks each, at most kMaxSlices of them
+    const int64_t per = T <= 8 ? T : (T + kMaxSlices - 1) / kMaxSlices < 4 ? 4 : (T + kMaxSlices - 1) / kMaxSlices;
+    int slice = 0;
+    for (int64_t t0 = 0; t0 < T; t0 += per, slice++) {
+        const int64_t t1 = t0 + per < T ? t0 + per : T;
+        const int64_t c0 = t0 * n, c1 = t1 * n < L ? t1 * n : L;     // sample columns of this slice
+        const size_t width = (size_t)(c1 - c0) * es;
+        const char* src = (const char*)audio + (size_t)c0 * es;
+        size_t spitch = (size_t)ld * es;
+        if (!audio_direct) {   // stage this slice's columns through pinned memory (rows packed at pitch L)
+            for (int b = 0; b < B; b++) memcpy(hp + o_audio + ((size_t)b * L + c0) * es, src + (size_t)b * spitch, width);
+            src = hp + o_audio + (size_t)c0 * es;
+            spitch = (size_t)L * es;
+        }
+        CUDA_TRY(cudaMemcpy2DAsync(dp + o_audio + (size_t)c0 * es, (size_t)L * es, src, spitch, width, (size_t)B, cudaMemcpyHostToDevice, sc));
+        cudaEvent_t ev = e->ev[slice % kMaxSlices];
+        CUDA_TRY(cudaEventRecord(ev, sc));
+        CUDA_TRY(cudaStreamWaitEvent(sk, ev, 0));
+        rc = forward_impl(e, sr, B, c1 - c0, L, dp + o_audio + (size_t)c0 * es, fmt, d_state, d_ctx, ctx, d_state, d_ctx, d_probs + t0, T, sk);
+        if (rc) return rc;
+    }
+    if (T > 0) CUDA_TRY(cudaMemcpyAsync(probs_direct ? (void*)probs : (void*)(hp + o_probs), d_probs, (size_t)B * T * 4, cudaMemcpyDeviceToHost, sk));
+    if (state_out) CUDA_TRY(cudaMemcpyAsync(hp + o_state, d_state, (size_t)2 * B * 128 * 4, cudaMemcpyDeviceToHost, sk));
+    if (ctx_out) CUDA_TRY(cudaMemcpyAsync(hp + o_ctx, d_ctx, (size_t)B * ctx * 4, cudaMemcpyDeviceToHost, sk));
+    CUDA_TRY(cudaStreamSynchronize(sk));
+    CUDA_TRY(cudaStreamSynchronize(sc));
+    if (T > 0 && !probs_direct)
+        for (int b = 0; b < B; b++) memcpy(probs + (size_t)b * ldp, hp + o_probs + (size_t)b * T * 4, (size_t)T * 4);
     if (state_out) memcpy(state_out, hp + o_state, (size_t)2 * B * 128 * 4);
     if (ctx_out) memcpy(ctx_out, hp + o_ctx, (size_t)B * ctx * 4);
     return SVAD_OK;
+}
+
+extern "C" int svad_forward_host(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const float* audio, const float* state_in,
+                                 const float* ctx_in, float* state_out, float* ctx_out, float* probs, int64_t ldp) {
+    return forward_host_impl(e, sr, B, L, ld, audio, kF32, state_in, ctx_in, state_out, ctx_out, probs, ldp);
+}
+extern "C" int svad_forward_host_pcm16(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const int16_t* audio, const float* state_in,
+                                       const float* ctx_in, float* state_out, float* ctx_out, float* probs, int64_t ldp) {
+    return forward_host_impl(e, sr, B, L, ld, audio, kI16, state_in, ctx_in, state_out, ctx_out, probs, ldp);
 }
 
 extern "C" int svad_step_host(svad_engine* e, int sr, int B, const float* input, const float* state_in, float* prob,
@@ -325,17 +381,18 @@ extern "C" int svad_step_host(svad_engine* e, int sr, int B, const float* input,
     if (!input || !prob) return fail(SVAD_EINVAL, "null input/prob");
     const int n = sr == 16000 ? 512 : 256, ctx = n / 8, W = ctx + n;
     CUDA_TRY(cudaSetDevice(e->device));
-    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t o_in = 0, o_state = al((size_t)B * W), o_prob = o_state + al((size_t)2 * B * 128), total = o_prob + al((size_t)B);
-    int rc = ensure_staging(e, total);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_in = 0, o_state = al((size_t)B * W * 4), o_prob = o_state + al((size_t)2 * B * 128 * 4), total = o_prob + al((size_t)B * 4);
+    int rc = ensure_staging(e, total, total);
     if (rc) return rc;
-    float *hp = e->h_pin, *dp = e->d_buf;
+    char *hp = (char*)e->h_pin, *dp = (char*)e->d_buf;
     memcpy(hp + o_in, input, (size_t)B * W * 4);
     if (state_in) memcpy(hp + o_state, state_in, (size_t)2 * B * 128 * 4);
     cudaStream_t st = e->stream;
     CUDA_TRY(cudaMemcpyAsync(dp + o_in, hp + o_in, (size_t)B * W * 4, cudaMemcpyHostToDevice, st));
     if (state_in) CUDA_TRY(cudaMemcpyAsync(dp + o_state, hp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyHostToDevice, st));
-    rc = svad_step_device(e, sr, B, dp + o_in, state_in ? dp + o_state : nullptr, dp + o_prob, state_out ? dp + o_state : nullptr, st);
+    rc = svad_step_device(e, sr, B, (const float*)(dp + o_in), state_in ? (const float*)(dp + o_state) : nullptr, (float*)(dp + o_prob),
+                          state_out ? (float*)(dp + o_state) : nullptr, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(hp + o_prob, dp + o_prob, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     if (state_out) CUDA_TRY(cudaMemcpyAsync(hp + o_state, dp + o_state, (size_t)2 * B * 128 * 4, cudaMemcpyDeviceToHost, st));

@@ -184,18 +184,31 @@ constexpr int binpos(int k) { return bitrev(k, ilog2(NP)); }
 // Sample `i` (0 <= i < L1 + N/4) of the padded window [context | chunk | reflect] of chunk t:
 //   utils_vad.py:78 (context concat), silero_vad.jit::_model.stft.padding (reflect right by N/4),
 //   utils_vad.py:100-102 (zero tail).  `ctx_in` (may be null) supplies samples before time 0.
-template <bool SR16>
-SVAD_HD float window_sample(const float* audio, long L, const float* ctx_in, long t, int i) {
+// Samples are fp32 in [-1, 1) or int16 PCM; PCM is scaled by 2^-15 on load, which is exactly the float the
+// reference's loaders produce (int16 / 32768: examples/cpp/wav.h:95-136, examples/onnx_sequence/run.py:115-119).
+SVAD_HD float ld_sample(const float* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+SVAD_HD float ld_sample(const int16_t* p) {
+#if defined(__CUDA_ARCH__)
+    return (float)__ldg(p) * (1.0f / 32768.0f);
+#else
+    return (float)*p * (1.0f / 32768.0f);
+#endif
+}
+
+template <bool SR16, typename S>
+SVAD_HD float window_sample(const S* audio, long L, const float* ctx_in, long t, int i) {
     using G = Geo<SR16>;
     if (i >= G::L1) i = 2 * G::L1 - 2 - i;           // xp[L1 + j] = x1[L1 - 2 - j]
     long a = t * G::n - G::ctx + i;
     if (a < 0) return ctx_in ? ctx_in[G::ctx + a] : 0.0f;
     if (a >= L) return 0.0f;
-#if defined(__CUDA_ARCH__)
-    return __ldg(audio + a);
-#else
-    return audio[a];
-#endif
+    return ld_sample(audio + a);
 }
 
 // ---------------------------------------------------------------- STFT pass A
@@ -212,8 +225,8 @@ SVAD_HD int zitem_fr(int item) { return (item >> 3) & 1; }
 // Raw (unwindowed) samples of one round for this thread: xa[q] = frame 2fp, xb[q] = frame 2fp+1, m = r + 16 q.
 // `fast` (CTA-uniform): the whole padded window of chunk t lies inside the row, so the addresses are affine in
 // (r, q) with the reflection resolved at compile time; otherwise the generic fetch handles context / zero tail.
-template <bool SR16>
-SVAD_HD void stft_load(int tid, int fp, const float* audio, const float* ctx_in, long L, long t, bool fast,
+template <bool SR16, typename S>
+SVAD_HD void stft_load(int tid, int fp, const S* audio, const float* ctx_in, long L, long t, bool fast,
                        float (&xa)[Geo<SR16>::NQ], float (&xb)[Geo<SR16>::NQ]) {
     using G = Geo<SR16>;
     const int r = tid & 15;
@@ -223,7 +236,7 @@ SVAD_HD void stft_load(int tid, int fp, const float* audio, const float* ctx_in,
         return;
     }
     if (fast) {
-        const float* p = audio + t * G::n - G::ctx;   // window origin
+        const S* p = audio + t * G::n - G::ctx;   // window origin
 #pragma unroll
         for (int q = 0; q < G::NQ; q++) {
             const int m = r + 16 * q;
@@ -231,20 +244,15 @@ SVAD_HD void stft_load(int tid, int fp, const float* audio, const float* ctx_in,
             // frame 3 runs into the reflect pad for m >= L1 - 3 hop (a multiple of 16, so independent of r)
             const bool refl = (fp == 1) && (16 * q >= G::L1 - 3 * G::hop);
             const int jb = refl ? 2 * G::L1 - 2 - ib : ib;
-#if defined(__CUDA_ARCH__)
-            xa[q] = __ldg(p + ia);
-            xb[q] = __ldg(p + jb);
-#else
-            xa[q] = p[ia];
-            xb[q] = p[jb];
-#endif
+            xa[q] = ld_sample(p + ia);
+            xb[q] = ld_sample(p + jb);
         }
     } else {
 #pragma unroll
         for (int q = 0; q < G::NQ; q++) {
             const int m = r + 16 * q;
-            xa[q] = window_sample<SR16>(audio, L, ctx_in, t, G::hop * (2 * fp) + m);
-            xb[q] = window_sample<SR16>(audio, L, ctx_in, t, G::hop * (2 * fp + 1) + m);
+            xa[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp) + m);
+            xb[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp + 1) + m);
         }
     }
 }

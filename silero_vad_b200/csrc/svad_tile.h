@@ -13,7 +13,7 @@
 namespace svad {
 
 struct TileArgs {
-    const float* audio;     // [B][ld] fp32, device (or host in the emulator)
+    const void* audio;      // [B][ld] samples (fp32 or int16 PCM, see run_cta's S), device (or host in the emulator)
     long ld, L;             // row stride, valid samples per row (tail is zero-padded to T*n)
     int B;                  // streams
     long T;                 // chunk steps = ceil(L / n)
@@ -28,12 +28,13 @@ struct TileArgs {
     const float* consts;    // SmemMap::consts_floats floats
 };
 
-template <bool SR16, int RM, class Env>
+template <bool SR16, int RM, typename S, class Env>
 SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_stride, int ntiles) {
     using G = Geo<SR16>;
     using TP = Tape<SR16>;
     const Tc tc(env.tid());
     float* sm = env.smem();
+    const S* audio = static_cast<const S*>(a.audio);
     Regs rg;
     constexpr int BT = 4 * RM;
 
@@ -81,14 +82,14 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                 rg.c[i * 2 + u] = v;
             }
         // audio rows of the two slots (one per 16-slot half) this thread feeds in STFT pass A
-        const float* aud[2];
+        const S* aud[2];
         const float* cxp[2];
 #pragma unroll
         for (int hs = 0; hs < 2; hs++) {
             const int sl = 16 * hs + (tc.tid >> 4);
             const int gs = g0 + slot_to_local<RM>(sl);
             const bool v = slot_valid<RM>(sl) && gs < a.B;
-            aud[hs] = v ? a.audio + (long)gs * a.ld : nullptr;
+            aud[hs] = v ? audio + (long)gs * a.ld : nullptr;
             cxp[hs] = (v && a.ctx_in) ? a.ctx_in + (long)gs * a.ctx_ld : nullptr;
         }
         env.sync();
@@ -100,18 +101,19 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
             const bool fast = (t > 0) && ((t + 1) * G::n <= a.L);
             if (t + 1 < a.T) {   // pull the next chunk of every stream of the tile into L2
 #pragma unroll
-                for (int i = tc.tid; i < BT * (G::n / 32); i += kThreads) {
-                    const int loc = i / (G::n / 32), line = i % (G::n / 32), g = g0 + loc;
-                    const long off = (t + 1) * G::n + line * 32;
-                    if (g < a.B && off < a.L) env.prefetch_l2(a.audio + (long)g * a.ld + off);
+                constexpr int kPerLine = 128 / (int)sizeof(S), kLines = G::n / kPerLine;
+                for (int i = tc.tid; i < BT * kLines; i += kThreads) {
+                    const int loc = i / kLines, line = i % kLines, g = g0 + loc;
+                    const long off = (t + 1) * G::n + line * kPerLine;
+                    if (g < a.B && off < a.L) env.prefetch_l2(audio + (long)g * a.ld + off);
                 }
             }
-            if (t == 0) stft_load<SR16>(tc.tid, 0, aud[0], cxp[0], a.L, t, fast, xa, xb);
+            if (t == 0) stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t, fast, xa, xb);
 #pragma unroll 1
             for (int rnd = 0; rnd < 4; rnd++) {
                 const int hs = rnd >> 1, fp = rnd & 1;
                 float na[G::NQ], nb[G::NQ];
-                if (rnd < 3) stft_load<SR16>(tc.tid, (rnd + 1) & 1, rnd >= 1 ? aud[1] : aud[0], rnd >= 1 ? cxp[1] : cxp[0], a.L, t, fast, na, nb);
+                if (rnd < 3) stft_load<SR16, S>(tc.tid, (rnd + 1) & 1, rnd >= 1 ? aud[1] : aud[0], rnd >= 1 ? cxp[1] : cxp[0], a.L, t, fast, na, nb);
                 stft_pass_a<SR16>(tc, sm, xa, xb);
                 env.sync();
 #pragma unroll
@@ -171,7 +173,7 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                 if (slot_valid<RM>(tc.tid) && g < a.B) a.probs[(long)g * a.ldp + t] = head_prob(sm, tc.tid);
             }
             if (t + 1 < a.T)
-                stft_load<SR16>(tc.tid, 0, aud[0], cxp[0], a.L, t + 1, ((t + 2) * G::n <= a.L), xa, xb);
+                stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t + 1, ((t + 2) * G::n <= a.L), xa, xb);
         }
         // ---- tile exit: carry state / context out
         env.sync();
@@ -197,7 +199,7 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                 if (g < a.B) {
                     // new context = last ctx samples of the (zero-padded) final window
                     const float* cx = a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr;
-                    float v = (a.T > 0) ? window_sample<SR16>(a.audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k)
+                    float v = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k)
                                         : (cx ? cx[k] : 0.0f);
                     a.ctx_out[(long)g * G::ctx + k] = v;
                 }

@@ -57,7 +57,11 @@ class SileroVADB200:
             raise ValueError("Input audio chunk is too short")
         return x, sr
 
-    def _to_device(self, x):
+    def _to_device(self, x, keep_pcm16=False):
+        if keep_pcm16 and x.dtype == torch.int16:
+            return x.to(device=self.device, non_blocking=True).contiguous()
+        if x.dtype == torch.int16:   # PCM -> [-1, 1) like the reference's loaders (int16 / 32768)
+            return x.to(device=self.device, non_blocking=True).to(torch.float32).mul_(1.0 / 32768.0).contiguous()
         return x.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
 
     def __call__(self, x, sr: int):
@@ -97,7 +101,8 @@ class SileroVADB200:
     # ------------------------------------------------------------------ extensions
     def audio_forward_device(self, x, sr: int, reset=True):
         """Like audio_forward but leaves the probabilities on the GPU; with reset=False continues from the
-        carried state/context (long streams fed in pieces whose length is a multiple of the chunk size)."""
+        carried state/context (long streams fed in pieces whose length is a multiple of the chunk size).
+        int16 tensors are taken as PCM and read by the kernel directly (half the bytes, same probabilities)."""
         x, sr = self._validate_input(x, sr)
         if reset:
             self.reset_states()
@@ -110,15 +115,16 @@ class SileroVADB200:
         if self._last_batch_size and self._last_batch_size != B:
             self.reset_states()
         with torch.cuda.device(self.device):
-            xd = self._to_device(x)
+            xd = self._to_device(x, keep_pcm16=True)
             if self._state is None:
                 self._state = torch.zeros(2, B, 128, device=self.device)
             if self._context is None:
                 self._context = torch.zeros(B, ctx, device=self.device)
             probs = torch.empty(B, T, device=self.device)
             st = torch.cuda.current_stream(self.device).cuda_stream
-            self.engine.forward_device(sr, B, L, xd.stride(0), _ptr(xd), _ptr(self._state), _ptr(self._context), _ptr(self._state),
-                                       _ptr(self._context), _ptr(probs), max(T, 1), st)
+            fwd = self.engine.forward_device_pcm16 if xd.dtype == torch.int16 else self.engine.forward_device
+            fwd(sr, B, L, xd.stride(0), _ptr(xd), _ptr(self._state), _ptr(self._context), _ptr(self._state),
+                _ptr(self._context), _ptr(probs), max(T, 1), st)
         self._last_sr = sr
         self._last_batch_size = B
         return probs

@@ -27,7 +27,7 @@ struct EmuEnv {
     int tid() const { return tid_; }
     float* smem() { return sh->smem.data(); }
     void sync() { pthread_barrier_wait(&sh->bar); }
-    void prefetch_l2(const float*) {}
+    void prefetch_l2(const void*) {}
     void issue(long it) {
         const int idx = (int)(it % Geo<SR16>::nslab), stage = (int)(it % kStages);
         memcpy(sh->smem.data() + SmemMap::stage + stage * SmemMap::stage_floats, sh->tape + Tape<SR16>::slab_off(idx),
@@ -39,7 +39,7 @@ struct EmuEnv {
     }
 };
 
-template <bool SR16, int RM>
+template <bool SR16, int RM, typename S>
 void run(const TileArgs& a, int ntiles) {
     Shared sh;
     sh.smem.assign(SmemMap::total_floats, 0.0f);
@@ -54,14 +54,14 @@ void run(const TileArgs& a, int ntiles) {
     for (int t = 0; t < kThreads; t++)
         th.emplace_back([&, t] {
             EmuEnv<SR16> env{&sh, t};
-            run_cta<SR16, RM>(env, a, 0, 1, ntiles);
+            run_cta<SR16, RM, S>(env, a, 0, 1, ntiles);
         });
     for (auto& x : th) x.join();
     pthread_barrier_destroy(&sh.bar);
 }
 }  // namespace
 
-extern "C" int svad_emu_forward(const char* weights, int sr, int rm, int B, long L, const float* audio, const float* state_in,
+extern "C" int svad_emu_forward(const char* weights, int sr, int rm, int B, long L, const void* audio, int pcm16, const float* state_in,
                                 const float* ctx_in, float* state_out, float* ctx_out, float* probs) {
     TensorMap tm;
     std::string err;
@@ -76,11 +76,11 @@ extern "C" int svad_emu_forward(const char* weights, int sr, int rm, int B, long
     a.probs = probs; a.ldp = a.T; a.tape = pb.tape.data(); a.consts = pb.consts.data();
     const int bt = 4 * rm, ntiles = (B + bt - 1) / bt;
     switch (rm * 2 + (sr16 ? 1 : 0)) {
-        case 9: run<true, 4>(a, ntiles); break;   case 8: run<false, 4>(a, ntiles); break;
-        case 11: run<true, 5>(a, ntiles); break;  case 10: run<false, 5>(a, ntiles); break;
-        case 13: run<true, 6>(a, ntiles); break;  case 12: run<false, 6>(a, ntiles); break;
-        case 15: run<true, 7>(a, ntiles); break;  case 14: run<false, 7>(a, ntiles); break;
-        case 17: run<true, 8>(a, ntiles); break;  case 16: run<false, 8>(a, ntiles); break;
+        case 9: pcm16 ? run<true, 4, int16_t>(a, ntiles) : run<true, 4, float>(a, ntiles); break;   case 8: pcm16 ? run<false, 4, int16_t>(a, ntiles) : run<false, 4, float>(a, ntiles); break;
+        case 11: pcm16 ? run<true, 5, int16_t>(a, ntiles) : run<true, 5, float>(a, ntiles); break;  case 10: pcm16 ? run<false, 5, int16_t>(a, ntiles) : run<false, 5, float>(a, ntiles); break;
+        case 13: pcm16 ? run<true, 6, int16_t>(a, ntiles) : run<true, 6, float>(a, ntiles); break;  case 12: pcm16 ? run<false, 6, int16_t>(a, ntiles) : run<false, 6, float>(a, ntiles); break;
+        case 15: pcm16 ? run<true, 7, int16_t>(a, ntiles) : run<true, 7, float>(a, ntiles); break;  case 14: pcm16 ? run<false, 7, int16_t>(a, ntiles) : run<false, 7, float>(a, ntiles); break;
+        case 17: pcm16 ? run<true, 8, int16_t>(a, ntiles) : run<true, 8, float>(a, ntiles); break;  case 16: pcm16 ? run<false, 8, int16_t>(a, ntiles) : run<false, 8, float>(a, ntiles); break;
         default: return -3;
     }
     return 0;

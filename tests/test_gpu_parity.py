@@ -200,3 +200,24 @@ def test_batch_timestamps_equal_single(torch_cuda, model, fixtures):
     got = get_speech_timestamps_batch(x, model, lengths=lens)
     for i, n in enumerate(lens):
         assert got[i] == get_speech_timestamps(x[i, :n], model), i
+
+
+def test_pcm16_paths_bit_identical(torch_cuda, model, fixtures):
+    """int16 PCM through the device and the (time-sliced, pipelined) host entry points == the fp32 path."""
+    torch = torch_cuda
+    pcm = torch.from_numpy(np.stack([fixtures["aepyx16k"]["pcm"][100000 * b: 100000 * b + 512 * 37 + 300] for b in range(9)]).copy())
+    f32 = pcm.to(torch.float32) / 32768.0
+    want = model.audio_forward(f32, 16000)
+    got = model.audio_forward(pcm, 16000)
+    assert torch.equal(want, got) and float(want.max()) > 0.9
+    B, L = pcm.shape
+    T = (L + 511) // 512
+    for arr, fn in ((pcm.numpy(), model.engine.forward_host_pcm16), (f32.numpy(), model.engine.forward_host)):
+        for pinned in (False, True):
+            a = torch.from_numpy(np.ascontiguousarray(arr))
+            a = a.pin_memory() if pinned else a
+            out = torch.zeros(B, T).pin_memory() if pinned else torch.zeros(B, T)
+            st = np.zeros((2, B, 128), np.float32)
+            fn(16000, B, L, L, a.data_ptr(), 0, 0, st.ctypes.data, 0, out.data_ptr(), T)
+            assert torch.equal(out.cpu(), want), (arr.dtype, pinned)
+            assert np.abs(st).max() > 0

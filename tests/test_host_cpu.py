@@ -100,7 +100,7 @@ def emu():
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", str(so), str(src)], check=True)
     lib = ctypes.CDLL(str(so))
     fp = ctypes.c_void_p
-    lib.svad_emu_forward.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long, fp, fp, fp, fp, fp, fp]
+    lib.svad_emu_forward.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long, fp, ctypes.c_int, fp, fp, fp, fp, fp]
     return lib
 
 
@@ -119,12 +119,26 @@ def test_emulated_kernel_matches_oracle(emu, oracle, fixtures, sr, rm, B):
     want = oracle.audio_forward(x, sr, state=st_o, context=cx_o, nthreads=2)
     probs = np.zeros_like(want)
     st_e, cx_e = np.zeros_like(st), np.zeros_like(cx)
-    rc = emu.svad_emu_forward(str(WEIGHTS).encode(), sr, rm, B, x.shape[1], x.ctypes.data, st.ctypes.data, cx.ctypes.data,
+    rc = emu.svad_emu_forward(str(WEIGHTS).encode(), sr, rm, B, x.shape[1], x.ctypes.data, 0, st.ctypes.data, cx.ctypes.data,
                               st_e.ctypes.data, cx_e.ctypes.data, probs.ctypes.data)
     assert rc == 0
     assert np.abs(probs - want).max() < 2e-5
     assert np.abs(st_e - st_o).max() < 2e-5
     assert np.array_equal(cx_e, cx_o)
+
+
+def test_emulated_kernel_pcm16_equals_f32(emu, fixtures):
+    """int16 PCM ingest (scaled by 2^-15 on load) must be bit-identical to feeding int16/32768 as fp32."""
+    from silero_vad_b200.model import WEIGHTS
+    pcm = np.stack([fixtures["test16k"]["pcm"][20000 * b: 20000 * b + 512 * 3 + 100] for b in range(3)]).copy()
+    f32 = pcm.astype(np.float32) / 32768.0
+    out = []
+    for arr, flag in ((f32, 0), (pcm, 1)):
+        p = np.zeros((3, 4), np.float32)
+        assert emu.svad_emu_forward(str(WEIGHTS).encode(), 16000, 7, 3, arr.shape[1], arr.ctypes.data, flag, None, None, None, None,
+                                    p.ctypes.data) == 0
+        out.append(p)
+    assert np.array_equal(out[0], out[1]) and out[0].max() > 0.5
 
 
 def test_validate_input_messages():
