@@ -106,7 +106,7 @@ def cpu_arm(args, threads=None, budget_s=12.0):
     bounded sample of the same workload (same sr, same synthetic recipe, fewer streams/chunks)."""
     from oracle.oracle import Oracle
     o = Oracle()
-    threads = threads or o.max_threads()
+    threads = threads or o.best_threads(args.sr)
     n = 512 if args.sr == 16000 else 256
     rng = np.random.default_rng(17 + args.sr)
     # calibrate: 8 streams/thread x 4 chunks
