@@ -28,7 +28,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 template <bool SR16>
 struct GpuEnv {
     float* sm;
-    uint64_t* full;  // [kStages] mbarriers
+    uint64_t* full;   // [kStages] "slab landed" mbarriers (TMA transaction count)
+    uint64_t* empty;  // [kStages] "slab consumed" mbarriers (one arrival per warp)
     const float* tape;
     int tid_;
     __device__ __forceinline__ int tid() const { return tid_; }
@@ -46,10 +47,7 @@ struct GpuEnv {
                      "l"(src), "r"(bytes), "r"(bar)
                      : "memory");
     }
-    __device__ __forceinline__ const float* slab_acquire(long it) {
-        const int stage = (int)(it % kStages);
-        const uint32_t parity = (uint32_t)((it / kStages) & 1);
-        const uint32_t bar = smem_u32(full + stage);
+    __device__ __forceinline__ static void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -61,10 +59,21 @@ struct GpuEnv {
             "}\n" ::"r"(bar),
             "r"(parity)
             : "memory");
+    }
+    __device__ __forceinline__ const float* slab_acquire(long it, long total) {
+        if (tid_ == 0 && it >= 1 && it + 1 < total) {
+            const long prev = it - 1;   // slab it+1 goes into the stage slab it-1 occupied
+            mbar_wait(smem_u32(empty + (prev % kStages)), (uint32_t)((prev / kStages) & 1));
+            issue(it + 1);
+        }
+        const int stage = (int)(it % kStages);
+        mbar_wait(smem_u32(full + stage), (uint32_t)((it / kStages) & 1));
         return sm + SmemMap::stage + stage * SmemMap::stage_floats;
     }
-    __device__ __forceinline__ void slab_release(long it, long total) {
-        if (tid_ == 0 && it + kStages < total) issue(it + kStages);
+    __device__ __forceinline__ void slab_done(long it) {   // one arrival per warp once all its lanes are done reading
+        __syncwarp();
+        if ((tid_ & 31) == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + (it % kStages))) : "memory");
     }
 };
 
@@ -75,12 +84,15 @@ __global__ void __launch_bounds__(kThreads, 1) svad_fused_fp32(TileArgs a, int n
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SmemMap::total_floats * 4);
-    GpuEnv<SR16> env{sm, full, a.tape, (int)threadIdx.x};
+    uint64_t* empty = full + kStages;
+    GpuEnv<SR16> env{sm, full, empty, a.tape, (int)threadIdx.x};
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++)
+        for (int s = 0; s < kStages; s++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(full + s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(empty + s)), "r"(kThreads / 32) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const long total = (long)my_tiles * a.T * Geo<SR16>::nslab;

@@ -35,8 +35,24 @@ constexpr int kGates = 512;
 constexpr int kStageBytes = 32768;  // one weight-tape slab buffer
 constexpr int kStages = 2;
 
+#if defined(__CUDACC__)
+using f4 = float4;
+using f2 = float2;
+#else
 struct alignas(16) f4 { float x, y, z, w; };
 struct alignas(8) f2 { float x, y; };
+#endif
+
+// Packed fp32 FMA (Blackwell FFMA2 / fma.rn.f32x2): {a, a} * b + c in one issue slot.  The fp32 pipe tops out at the
+// same ~110 FMA/clk/SM either way (tools/ubench_fma.cu), but FFMA2 needs half the issue slots, which is what the
+// operand loads and address arithmetic of the GEMM loops compete for.  Per-lane results are IEEE fmaf.
+SVAD_HD f2 ffma2_s(float a, f2 b, f2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(make_float2(a, a), b, c);
+#else
+    return f2{fmaf(a, b.x, c.x), fmaf(a, b.y, c.y)};
+#endif
+}
 
 // ---------------------------------------------------------------- branch geometry
 template <bool SR16>
@@ -104,7 +120,7 @@ SVAD_HD int slot_to_local(int s) {  // local stream index of a valid slot
 
 // ---------------------------------------------------------------- persistent per-thread registers
 struct Regs {
-    float acc[64];   // GEMM accumulators of the current layer
+    f2 acc[32];      // GEMM accumulators of the current layer (column or row pairs, see each layer)
     float c[16];     // LSTM cell state: [row i][unit u] -> c[i*2+u]
 };
 
@@ -339,86 +355,113 @@ SVAD_HD float relu(float v) { return v > 0.0f ? v : 0.0f; }   // NaN -> 0 like f
 SVAD_HD float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
 
 // ---------------------------------------------------------------- enc0
-// acc[t][i][u] (t<4 frames, i<8 rows, u<2 cols) -> rg.acc[(t*8+i)*2+u]; cols 16*warp + 2*ln + u.
+// acc[t][i] = (col u=0, col u=1) for t<4 frames, i<8 rows -> rg.acc[t*8+i]; cols 16*warp + 2*ln + u.
 // slab = W0p[c][j][128] for channels [c0, c1).
 template <bool SR16, int RM>
 SVAD_HD void enc0_init(const Tc& tc, const float* sm, Regs& rg) {
-    const float* b0 = sm + SmemMap::consts + SmemMap::c_b0 + 16 * tc.warp + 2 * tc.ln;
+    const f2 b0 = *reinterpret_cast<const f2*>(sm + SmemMap::consts + SmemMap::c_b0 + 16 * tc.warp + 2 * tc.ln);
+#pragma unroll
+    for (int k = 0; k < 32; k++) rg.acc[k] = b0;
+}
+template <bool SR16>
+SVAD_HD void enc0_fetch(const Tc& tc, const float* mag, const float* wp, int c, float (&x)[4][8], f2 (&w)[3]) {
+    using G = Geo<SR16>;
+#pragma unroll
+    for (int f = 0; f < 4; f++) load8(mag + (f * G::F + c) * kSlots, tc.lm, 0, x[f]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) w[j] = *reinterpret_cast<const f2*>(wp + j * 128);
+}
+template <int RM>
+SVAD_HD void enc0_fma(const float (&x)[4][8], const f2 (&w)[3], Regs& rg) {
 #pragma unroll
     for (int t = 0; t < 4; t++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) { rg.acc[(t * 8 + i) * 2] = b0[0]; rg.acc[(t * 8 + i) * 2 + 1] = b0[1]; }
+        for (int j = 0; j < 3; j++) {
+            const int fi = t + j - 1;
+            if (fi < 0 || fi > 3) continue;
+#pragma unroll
+            for (int i = 0; i < RM; i++) rg.acc[t * 8 + i] = ffma2_s(x[fi][i], w[j], rg.acc[t * 8 + i]);
+        }
 }
+// Operands of channel c+1 are fetched before the 70-80 FFMA2 of channel c issue (register double buffer), so a
+// warp never sits on LDS latency with an idle FMA pipe even when its SMSP partner runs in lockstep.
 template <bool SR16, int RM>
 SVAD_HD void enc0_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int c0, int c1) {
-    using G = Geo<SR16>;
     const int oc = 16 * tc.warp + 2 * tc.ln;
     const float* mag = sm + SmemMap::mag;
+    const float* wp = slab + oc;
+    float xa[4][8], xb[4][8];
+    f2 wa[3], wb[3];
+    enc0_fetch<SR16>(tc, mag, wp, c0, xa, wa);
+    int c = c0;
 #pragma unroll 1
-    for (int c = c0; c < c1; c++) {
-        float x[4][8];
-#pragma unroll
-        for (int f = 0; f < 4; f++) load8(mag + (f * G::F + c) * kSlots, tc.lm, 0, x[f]);
-        const float* wp = slab + (c - c0) * 384 + oc;
-        f2 w[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) w[j] = *reinterpret_cast<const f2*>(wp + j * 128);
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const int fi = t + j - 1;
-                if (fi < 0 || fi > 3) continue;
-#pragma unroll
-                for (int i = 0; i < RM; i++) {
-                    rg.acc[(t * 8 + i) * 2] = fmaf(w[j].x, x[fi][i], rg.acc[(t * 8 + i) * 2]);
-                    rg.acc[(t * 8 + i) * 2 + 1] = fmaf(w[j].y, x[fi][i], rg.acc[(t * 8 + i) * 2 + 1]);
-                }
-            }
+    for (; c + 2 <= c1; c += 2) {
+        enc0_fetch<SR16>(tc, mag, wp + (c + 1 - c0) * 384, c + 1, xb, wb);
+        enc0_fma<RM>(xa, wa, rg);
+        if (c + 2 < c1) enc0_fetch<SR16>(tc, mag, wp + (c + 2 - c0) * 384, c + 2, xa, wa);
+        enc0_fma<RM>(xb, wb, rg);
     }
+    if (c < c1) enc0_fma<RM>(xa, wa, rg);
 }
 template <bool SR16, int RM>
 SVAD_HD void enc0_store(const Tc& tc, float* sm, const Regs& rg) {
     const int oc = 16 * tc.warp + 2 * tc.ln;
 #pragma unroll
-    for (int t = 0; t < 4; t++)
+    for (int t = 0; t < 4; t++) {
+        float v0[8], v1[8];
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(rg.acc[(t * 8 + i) * 2 + u]) : 0.0f;
-            store8(sm + SmemMap::e0 + (t * 128 + oc + u) * kSlots, tc.lm, key_hi(oc), v);
+        for (int i = 0; i < 8; i++) {
+            v0[i] = (i < RM) ? relu(rg.acc[t * 8 + i].x) : 0.0f;
+            v1[i] = (i < RM) ? relu(rg.acc[t * 8 + i].y) : 0.0f;
         }
+        store8(sm + SmemMap::e0 + (t * 128 + oc) * kSlots, tc.lm, key_hi(oc), v0);
+        store8(sm + SmemMap::e0 + (t * 128 + oc + 1) * kSlots, tc.lm, key_hi(oc), v1);
+    }
 }
 
 // ---------------------------------------------------------------- enc1: 128 -> 64, stride 2, T 4 -> 2
-// acc[t][i] -> rg.acc[t*8+i]; col o = 8*warp + ln.  slab = W1p[c][j][64] for channels [c0, c1).
-// t=0 sees frames (-1,0,1) -> taps 1,2 ; t=1 sees frames (1,2,3).
+// One output column o = 8*warp + ln per thread; accumulators are ROW pairs: rg.acc[t*4 + ip] = rows (2ip, 2ip+1).
+// slab = W1p[c][j][64] for channels [c0, c1).  t=0 sees frames (-1,0,1) -> taps 1,2 ; t=1 sees frames (1,2,3).
+// (With RM = 7 the unused 8th row is computed along: its inputs are finite zeros/garbage of an invalid slot.)
+SVAD_HD void load8p(const float* row, int lm, int key, f2 (&x)[4]) {
+    f4 a = *reinterpret_cast<const f4*>(row + ((lm ^ key) << 2));
+    f4 b = *reinterpret_cast<const f4*>(row + (((4 + lm) ^ key) << 2));
+    x[0] = f2{a.x, a.y}; x[1] = f2{a.z, a.w}; x[2] = f2{b.x, b.y}; x[3] = f2{b.z, b.w};
+}
 template <int RM>
 SVAD_HD void enc1_init(const Tc& tc, const float* sm, Regs& rg) {
-    float b = sm[SmemMap::consts + SmemMap::c_b1 + 8 * tc.warp + tc.ln];
+    const float b = sm[SmemMap::consts + SmemMap::c_b1 + 8 * tc.warp + tc.ln];
 #pragma unroll
-    for (int k = 0; k < 16; k++) rg.acc[k] = b;
+    for (int k = 0; k < 8; k++) rg.acc[k] = f2{b, b};
+}
+SVAD_HD void enc1_fetch(const Tc& tc, const float* e0, const float* wp, int c, f2 (&x)[4][4], float (&w)[3]) {
+#pragma unroll
+    for (int f = 0; f < 4; f++) load8p(e0 + (f * 128 + c) * kSlots, tc.lm, key_hi(c), x[f]);
+    w[0] = wp[0]; w[1] = wp[64]; w[2] = wp[128];
+}
+SVAD_HD void enc1_fma(const f2 (&x)[4][4], const float (&w)[3], Regs& rg) {
+#pragma unroll
+    for (int ip = 0; ip < 4; ip++) {
+        rg.acc[ip] = ffma2_s(w[1], x[0][ip], rg.acc[ip]);
+        rg.acc[ip] = ffma2_s(w[2], x[1][ip], rg.acc[ip]);
+        rg.acc[4 + ip] = ffma2_s(w[0], x[1][ip], rg.acc[4 + ip]);
+        rg.acc[4 + ip] = ffma2_s(w[1], x[2][ip], rg.acc[4 + ip]);
+        rg.acc[4 + ip] = ffma2_s(w[2], x[3][ip], rg.acc[4 + ip]);
+    }
 }
 template <int RM>
 SVAD_HD void enc1_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int c0, int c1) {
-    const int o = 8 * tc.warp + tc.ln;
+    const float* wp = slab + 8 * tc.warp + tc.ln;
     const float* e0 = sm + SmemMap::e0;
+    f2 xa[4][4], xb[4][4];
+    float wa[3], wb[3];
+    enc1_fetch(tc, e0, wp, c0, xa, wa);
 #pragma unroll 2
-    for (int c = c0; c < c1; c++) {
-        float x[4][8];
-#pragma unroll
-        for (int f = 0; f < 4; f++) load8(e0 + (f * 128 + c) * kSlots, tc.lm, key_hi(c), x[f]);
-        const float* wp = slab + (c - c0) * 192 + o;
-        const float w0 = wp[0], w1 = wp[64], w2 = wp[128];
-#pragma unroll
-        for (int i = 0; i < RM; i++) {
-            rg.acc[i] = fmaf(w1, x[0][i], rg.acc[i]);
-            rg.acc[i] = fmaf(w2, x[1][i], rg.acc[i]);
-            rg.acc[8 + i] = fmaf(w0, x[1][i], rg.acc[8 + i]);
-            rg.acc[8 + i] = fmaf(w1, x[2][i], rg.acc[8 + i]);
-            rg.acc[8 + i] = fmaf(w2, x[3][i], rg.acc[8 + i]);
-        }
+    for (int c = c0; c < c1; c += 2) {   // slabs hold an even number of channels (32)
+        enc1_fetch(tc, e0, wp + (c + 1 - c0) * 192, c + 1, xb, wb);
+        enc1_fma(xa, wa, rg);
+        if (c + 2 < c1) enc1_fetch(tc, e0, wp + (c + 2 - c0) * 192, c + 2, xa, wa);
+        enc1_fma(xb, wb, rg);
     }
 }
 template <int RM>
@@ -428,91 +471,107 @@ SVAD_HD void enc1_store(const Tc& tc, float* sm, const Regs& rg) {
     for (int t = 0; t < 2; t++) {
         float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(rg.acc[t * 8 + i]) : 0.0f;
+        for (int ip = 0; ip < 4; ip++) {
+            v[2 * ip] = (2 * ip < RM) ? relu(rg.acc[t * 4 + ip].x) : 0.0f;
+            v[2 * ip + 1] = (2 * ip + 1 < RM) ? relu(rg.acc[t * 4 + ip].y) : 0.0f;
+        }
         store8(sm + SmemMap::e1 + (t * 64 + o) * kSlots, tc.lm, key_lo(o), v);
     }
 }
 
 // ---------------------------------------------------------------- enc2: 64 -> 64, stride 2, T 2 -> 1 (taps 1,2 live)
-// slab = W2p[c][jj][64], jj=0 <-> tap 1 (frame 0), jj=1 <-> tap 2 (frame 1); one slab, 64 channels.
+// slab = W2p[c][jj][64], jj=0 <-> tap 1 (frame 0), jj=1 <-> tap 2 (frame 1); one slab, 64 channels.  Row pairs.
 template <int RM>
 SVAD_HD void enc2_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
     const int o = 8 * tc.warp + tc.ln;
-    float b = sm[SmemMap::consts + SmemMap::c_b2 + o];
-    float acc[8];
+    const float b = sm[SmemMap::consts + SmemMap::c_b2 + o];
+    f2 acc[4];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = b;
+    for (int ip = 0; ip < 4; ip++) acc[ip] = f2{b, b};
 #pragma unroll 4
     for (int c = 0; c < 64; c++) {
-        float x0[8], x1[8];
-        load8(sm + SmemMap::e1 + c * kSlots, tc.lm, key_lo(c), x0);
-        load8(sm + SmemMap::e1 + (64 + c) * kSlots, tc.lm, key_lo(c), x1);
+        f2 x0[4], x1[4];
+        load8p(sm + SmemMap::e1 + c * kSlots, tc.lm, key_lo(c), x0);
+        load8p(sm + SmemMap::e1 + (64 + c) * kSlots, tc.lm, key_lo(c), x1);
         const float w0 = slab[c * 128 + o], w1 = slab[c * 128 + 64 + o];
 #pragma unroll
-        for (int i = 0; i < RM; i++) { acc[i] = fmaf(w0, x0[i], acc[i]); acc[i] = fmaf(w1, x1[i], acc[i]); }
+        for (int ip = 0; ip < 4; ip++) { acc[ip] = ffma2_s(w0, x0[ip], acc[ip]); acc[ip] = ffma2_s(w1, x1[ip], acc[ip]); }
     }
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(acc[i]) : 0.0f;
+    for (int ip = 0; ip < 4; ip++) {
+        v[2 * ip] = (2 * ip < RM) ? relu(acc[ip].x) : 0.0f;
+        v[2 * ip + 1] = (2 * ip + 1 < RM) ? relu(acc[ip].y) : 0.0f;
+    }
     store8(sm + SmemMap::e2 + o * kSlots, tc.lm, key_lo(o), v);
     (void)rg;
 }
 
 // ---------------------------------------------------------------- enc3: 64 -> 128, T 1 -> 1 (tap 1 live)
-// slab = W3p[c][128]; cols 16*warp + 2*ln + u.
+// slab = W3p[c][128]; cols 16*warp + 2*ln + u (column pairs).
 template <int RM>
 SVAD_HD void enc3_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
     const int oc = 16 * tc.warp + 2 * tc.ln;
-    const float* b3 = sm + SmemMap::consts + SmemMap::c_b3 + oc;
-    float acc[8][2];
+    const f2 b3 = *reinterpret_cast<const f2*>(sm + SmemMap::consts + SmemMap::c_b3 + oc);
+    f2 acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { acc[i][0] = b3[0]; acc[i][1] = b3[1]; }
+    for (int i = 0; i < 8; i++) acc[i] = b3;
 #pragma unroll 4
     for (int c = 0; c < 64; c++) {
         float x[8];
         load8(sm + SmemMap::e2 + c * kSlots, tc.lm, key_lo(c), x);
-        f2 w = *reinterpret_cast<const f2*>(slab + c * 128 + oc);
+        const f2 w = *reinterpret_cast<const f2*>(slab + c * 128 + oc);
 #pragma unroll
-        for (int i = 0; i < RM; i++) { acc[i][0] = fmaf(w.x, x[i], acc[i][0]); acc[i][1] = fmaf(w.y, x[i], acc[i][1]); }
+        for (int i = 0; i < RM; i++) acc[i] = ffma2_s(x[i], w, acc[i]);
     }
+    float v0[8], v1[8];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = (i < RM) ? relu(acc[i][u]) : 0.0f;
-        store8(sm + SmemMap::e3 + (oc + u) * kSlots, tc.lm, key_hi(oc), v);
-    }
+    for (int i = 0; i < 8; i++) { v0[i] = (i < RM) ? relu(acc[i].x) : 0.0f; v1[i] = (i < RM) ? relu(acc[i].y) : 0.0f; }
+    store8(sm + SmemMap::e3 + oc * kSlots, tc.lm, key_hi(oc), v0);
+    store8(sm + SmemMap::e3 + (oc + 1) * kSlots, tc.lm, key_hi(oc), v1);
     (void)rg;
 }
 
 // ---------------------------------------------------------------- LSTM
 // Columns are permuted on the host: n' = 64*warp + 32*u + 4*ln + g  <->  gate g of hidden unit j = 16*warp + 2*ln + u.
-// acc[i][u*4+g] -> rg.acc[i*8 + u*4 + g].  slab = Wl[k][512] for k in [k0, k0+16); k < 128 reads e3, else h.
+// rg.acc[i*4 + 2u + p] = gates (2p, 2p+1) of unit u for row i.  slab = Wl[k][512] for k in [k0, k0+16);
+// k < 128 reads e3, else h.
 template <int RM>
 SVAD_HD void lstm_init(const Tc& tc, const float* sm, Regs& rg) {
     const float* bl = sm + SmemMap::consts + SmemMap::c_bl + 64 * tc.warp + 4 * tc.ln;
-    f4 b0 = *reinterpret_cast<const f4*>(bl), b1 = *reinterpret_cast<const f4*>(bl + 32);
+    const f4 b0 = *reinterpret_cast<const f4*>(bl), b1 = *reinterpret_cast<const f4*>(bl + 32);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        rg.acc[i * 8 + 0] = b0.x; rg.acc[i * 8 + 1] = b0.y; rg.acc[i * 8 + 2] = b0.z; rg.acc[i * 8 + 3] = b0.w;
-        rg.acc[i * 8 + 4] = b1.x; rg.acc[i * 8 + 5] = b1.y; rg.acc[i * 8 + 6] = b1.z; rg.acc[i * 8 + 7] = b1.w;
+        rg.acc[i * 4 + 0] = f2{b0.x, b0.y}; rg.acc[i * 4 + 1] = f2{b0.z, b0.w};
+        rg.acc[i * 4 + 2] = f2{b1.x, b1.y}; rg.acc[i * 4 + 3] = f2{b1.z, b1.w};
     }
+}
+SVAD_HD void lstm_fetch(const Tc& tc, const float* a, const float* wrow, int kk, float (&x)[8], f2 (&w)[4]) {
+    load8(a + kk * kSlots, tc.lm, key_hi(kk), x);
+    const f4 w0 = *reinterpret_cast<const f4*>(wrow + kk * kGates);
+    const f4 w1 = *reinterpret_cast<const f4*>(wrow + kk * kGates + 32);
+    w[0] = f2{w0.x, w0.y}; w[1] = f2{w0.z, w0.w}; w[2] = f2{w1.x, w1.y}; w[3] = f2{w1.z, w1.w};
+}
+template <int RM>
+SVAD_HD void lstm_fma(const float (&x)[8], const f2 (&w)[4], Regs& rg) {
+#pragma unroll
+    for (int i = 0; i < RM; i++)
+#pragma unroll
+        for (int p = 0; p < 4; p++) rg.acc[i * 4 + p] = ffma2_s(x[i], w[p], rg.acc[i * 4 + p]);
 }
 template <int RM>
 SVAD_HD void lstm_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int k0) {
-    const int nc = 64 * tc.warp + 4 * tc.ln;
+    const float* wrow = slab + 64 * tc.warp + 4 * tc.ln;
     const float* a = (k0 < kHid) ? sm + SmemMap::e3 + k0 * kSlots : sm + SmemMap::h + (k0 - kHid) * kSlots;
-#pragma unroll 4
-    for (int kk = 0; kk < 16; kk++) {
-        float x[8];
-        load8(a + kk * kSlots, tc.lm, key_hi(kk), x);
-        f4 w0 = *reinterpret_cast<const f4*>(slab + kk * kGates + nc);
-        f4 w1 = *reinterpret_cast<const f4*>(slab + kk * kGates + nc + 32);
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int i = 0; i < RM; i++)
-#pragma unroll
-            for (int n = 0; n < 8; n++) rg.acc[i * 8 + n] = fmaf(w[n], x[i], rg.acc[i * 8 + n]);
+    float xa[8], xb[8];
+    f2 wa[4], wb[4];
+    lstm_fetch(tc, a, wrow, 0, xa, wa);
+#pragma unroll 2
+    for (int kk = 0; kk < 16; kk += 2) {
+        lstm_fetch(tc, a, wrow, kk + 1, xb, wb);
+        lstm_fma<RM>(xa, wa, rg);
+        if (kk + 2 < 16) lstm_fetch(tc, a, wrow, kk + 2, xa, wa);
+        lstm_fma<RM>(xb, wb, rg);
     }
 }
 // gate nonlinearity + state update; writes h' into smem (after the barrier that ends the last slab).
@@ -525,8 +584,8 @@ SVAD_HD void lstm_epilogue(const Tc& tc, float* sm, Regs& rg) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             if (i < RM) {
-                const float* g = rg.acc + i * 8 + u * 4;
-                float ig = sigmoid_acc(g[0]), fg = sigmoid_acc(g[1]), gg = tanhf(g[2]), og = sigmoid_acc(g[3]);
+                const f2 g01 = rg.acc[i * 4 + 2 * u], g23 = rg.acc[i * 4 + 2 * u + 1];
+                float ig = sigmoid_acc(g01.x), fg = sigmoid_acc(g01.y), gg = tanhf(g23.x), og = sigmoid_acc(g23.y);
                 float cn = fmaf(fg, rg.c[i * 2 + u], ig * gg);
                 rg.c[i * 2 + u] = cn;
                 hv[i] = og * tanhf(cn);

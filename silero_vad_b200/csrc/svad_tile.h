@@ -3,9 +3,13 @@
 //
 // `Env` hides what differs between the GPU and the CPU emulator:
 //   int tid();  float* smem();  void sync();                      CTA barrier
-//   const float* slab_acquire(long it);                           wait until tape slab #it is in its stage
-//   void slab_release(long it, long total);                       (after a sync) thread 0 refills the stage
-// Per step and tile: 8 barriers for the STFT, one per weight slab, 3 around the LSTM epilogue / head.
+//   const float* slab_acquire(long it, long total);               thread 0 first refills the ring (waits until every warp
+//                                                                 released slab it-1, issues slab it+1); then all wait
+//                                                                 until tape slab #it has landed in its stage
+//   void slab_done(long it);                                      this thread is finished reading slab #it
+// Weight slabs are handed over with full/empty mbarriers, so warps are NOT barrier-synchronised per slab; CTA
+// barriers remain only where activations cross threads: 8 for the STFT, one per layer boundary, 2 around the
+// LSTM epilogue / head (15 per step instead of 45).
 #pragma once
 #include "svad_core.h"
 #include "svad_pack.h"
@@ -128,44 +132,44 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
             enc0_init<SR16, RM>(tc, sm, rg);
 #pragma unroll 1
             for (int s = 0; s < G::e0_nslab; s++, it++) {
-                const float* slab = env.slab_acquire(it);
+                const float* slab = env.slab_acquire(it, total_slabs);
                 enc0_slab<SR16, RM>(tc, sm, slab, rg, TP::e0_c0(s), TP::e0_c0(s + 1));
-                if (s == G::e0_nslab - 1) enc0_store<SR16, RM>(tc, sm, rg);
-                env.sync();
-                env.slab_release(it, total_slabs);
+                env.slab_done(it);
             }
+            enc0_store<SR16, RM>(tc, sm, rg);
+            env.sync();
             // ---------------- enc1
             enc1_init<RM>(tc, sm, rg);
 #pragma unroll 1
             for (int s = 0; s < 4; s++, it++) {
-                const float* slab = env.slab_acquire(it);
+                const float* slab = env.slab_acquire(it, total_slabs);
                 enc1_slab<RM>(tc, sm, slab, rg, s * 32, s * 32 + 32);
-                if (s == 3) enc1_store<RM>(tc, sm, rg);
-                env.sync();
-                env.slab_release(it, total_slabs);
+                env.slab_done(it);
             }
+            enc1_store<RM>(tc, sm, rg);
+            env.sync();
             // ---------------- enc2, enc3
             {
-                const float* slab = env.slab_acquire(it);
+                const float* slab = env.slab_acquire(it, total_slabs);
                 enc2_all<RM>(tc, sm, slab, rg);
+                env.slab_done(it);
                 env.sync();
-                env.slab_release(it, total_slabs);
                 it++;
-                slab = env.slab_acquire(it);
+                slab = env.slab_acquire(it, total_slabs);
                 enc3_all<RM>(tc, sm, slab, rg);
+                env.slab_done(it);
                 env.sync();
-                env.slab_release(it, total_slabs);
                 it++;
             }
             // ---------------- LSTM + head
             lstm_init<RM>(tc, sm, rg);
 #pragma unroll 1
             for (int s = 0; s < 16; s++, it++) {
-                const float* slab = env.slab_acquire(it);
+                const float* slab = env.slab_acquire(it, total_slabs);
                 lstm_slab<RM>(tc, sm, slab, rg, s * 16);
-                env.sync();
-                env.slab_release(it, total_slabs);
+                env.slab_done(it);
             }
+            env.sync();   // every warp is done reading e3 / h
             lstm_epilogue<RM>(tc, sm, rg);
             env.sync();
             if (tc.tid < kSlots) {

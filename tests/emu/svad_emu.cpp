@@ -4,6 +4,9 @@
 // TMA bulk copies of weight slabs.  Lets the layout / index algebra be checked against the oracle
 // in the build container, which has no GPU.  Not part of the product; never timed.
 #include <pthread.h>
+#include <sched.h>
+
+#include <atomic>
 
 #include <cstdlib>
 #include <string>
@@ -19,6 +22,8 @@ struct Shared {
     std::vector<float> smem;
     pthread_barrier_t bar;
     const float* tape;
+    std::atomic<long> issued{0};                 // slabs copied into the ring so far (the "full" side)
+    std::atomic<long> released[kStages];         // per stage: thread arrivals so far (the "empty" side)
 };
 template <bool SR16>
 struct EmuEnv {
@@ -33,10 +38,17 @@ struct EmuEnv {
         memcpy(sh->smem.data() + SmemMap::stage + stage * SmemMap::stage_floats, sh->tape + Tape<SR16>::slab_off(idx),
                sizeof(float) * Tape<SR16>::slab_len(idx));
     }
-    const float* slab_acquire(long it) { return sh->smem.data() + SmemMap::stage + (it % kStages) * SmemMap::stage_floats; }
-    void slab_release(long it, long total) {
-        if (tid_ == 0 && it + kStages < total) issue(it + kStages);
+    const float* slab_acquire(long it, long total) {
+        if (tid_ == 0 && it >= 1 && it + 1 < total) {
+            const long prev = it - 1;   // its stage is the one slab it+1 goes into
+            while (sh->released[prev % kStages].load(std::memory_order_acquire) < (long)kThreads * (prev / kStages + 1)) sched_yield();
+            issue(it + 1);
+            sh->issued.store(it + 2, std::memory_order_release);
+        }
+        while (sh->issued.load(std::memory_order_acquire) <= it) sched_yield();
+        return sh->smem.data() + SmemMap::stage + (it % kStages) * SmemMap::stage_floats;
     }
+    void slab_done(long it) { sh->released[it % kStages].fetch_add(1, std::memory_order_acq_rel); }
 };
 
 template <bool SR16, int RM, typename S>
@@ -48,7 +60,10 @@ void run(const TileArgs& a, int ntiles) {
     {
         EmuEnv<SR16> e0{&sh, 0};
         const long total = (long)ntiles * a.T * Geo<SR16>::nslab;
-        for (long i = 0; i < kStages && i < total; i++) e0.issue(i);
+        for (int i = 0; i < kStages; i++) sh.released[i] = 0;
+        long pre = 0;
+        for (long i = 0; i < kStages && i < total; i++) { e0.issue(i); pre = i + 1; }
+        sh.issued = pre;
     }
     std::vector<std::thread> th;
     for (int t = 0; t < kThreads; t++)
