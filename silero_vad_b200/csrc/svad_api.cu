@@ -16,7 +16,7 @@
 #include <string>
 
 #include "../../include/silero_vad_b200.h"
-#include "svad_tile.h"
+#include "svad_tc.h"
 
 using namespace svad;
 
@@ -102,6 +102,157 @@ __global__ void __launch_bounds__(kThreads, 1) svad_fused_fp32(TileArgs a, int n
     run_cta<SR16, RM, S>(env, a, (int)blockIdx.x, (int)gridDim.x, ntiles);
 }
 
+
+// ------------------------------------------------------------------------------------------ tensor-core kernel
+// Shared-memory matrix descriptor (tcgen05): start address, leading / stride byte offsets (>>4), version 1,
+// layout type 2 = SWIZZLE_128B (K-major weight tiles), 1 = SWIZZLE_128B_BASE32B (MN-major tf32 activation rows).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+// instruction descriptor: D fp32, A/B tf32, A K-major, B MN-major, N = 32, M = 128
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kTmemCols = 256;
+
+template <bool SR16>
+struct GpuEnvTC {
+    float* sm;
+    uint64_t* full;    // [kStages] slab landed (TMA tx)
+    uint64_t* mdone;   // [kStages] MMAs that read the stage have completed (tcgen05.commit)
+    uint64_t* accb;    // layer accumulators complete
+    const float* tape;
+    int tid_;
+    uint32_t tmem;
+    long issued, freed;
+    uint32_t mcnt0, mcnt1, acc_phase;
+    __device__ __forceinline__ int tid() const { return tid_; }
+    __device__ __forceinline__ float* smem() { return sm; }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void warp_sync() { __syncwarp(); }
+    __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+    __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+    __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+    __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+    __device__ __forceinline__ static void mbar_wait(uint32_t bar, uint32_t parity) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+    }
+    __device__ __forceinline__ void issue(long it) {
+        const int idx = (int)(it % TapeTC<SR16>::nslab), stage = (int)(it % kStages);
+        const uint32_t bytes = (uint32_t)TapeTC<SR16>::slab_len(idx) * 4u;
+        const uint32_t bar = smem_u32(full + stage);
+        const uint32_t dst = smem_u32(sm + SmemMapTC::stage + stage * SmemMapTC::stage_floats);
+        const float* src = tape + TapeTC<SR16>::slab_off(idx);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+    __device__ __forceinline__ const float* slab_wait(long it) {
+        const int stage = (int)(it % kStages);
+        mbar_wait(smem_u32(full + stage), (uint32_t)((it / kStages) & 1));
+        return sm + SmemMapTC::stage + stage * SmemMapTC::stage_floats;
+    }
+    __device__ __forceinline__ static bool is_mma_slab(long it) {
+        const int idx = (int)(it % TapeTC<SR16>::nslab);
+        return idx < TapeTC<SR16>::e0_nslab || idx >= TapeTC<SR16>::e0_nslab + 6;
+    }
+    __device__ __forceinline__ void mark_free(long x) { freed = x; }
+    __device__ __forceinline__ void free_upto(long x) {
+        for (long y = freed + 1; y <= x; y++) {
+            if (is_mma_slab(y)) {
+                if (y & 1) { mbar_wait(smem_u32(mdone + 1), mcnt1 & 1); mcnt1++; }
+                else { mbar_wait(smem_u32(mdone), mcnt0 & 1); mcnt0++; }
+            }
+        }
+        if (x > freed) freed = x;
+    }
+    __device__ __forceinline__ void refill_upto(long x, long total) {
+        while (issued <= x && issued < total) { issue(issued); issued++; }
+    }
+    __device__ __forceinline__ void mma(int col, const float* a_tile, int ks, const float* b_rows, bool acc) {
+        const uint64_t ad = umma_desc(smem_u32(a_tile) + ks * 32, 16, 1024, 2);
+        const uint64_t bd = umma_desc(smem_u32(b_rows), 4096, 512, 1);
+        const uint32_t accf = acc ? 1u : 0u;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem + (uint32_t)col),
+            "l"(ad), "l"(bd), "r"(kIdescTf32), "r"(accf)
+            : "memory");
+    }
+    __device__ __forceinline__ void mma_slab_done(long it) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mdone + (it % kStages))) : "memory");
+    }
+    __device__ __forceinline__ void acc_commit() {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(accb)) : "memory");
+    }
+    __device__ __forceinline__ void acc_wait() {
+        mbar_wait(smem_u32(accb), acc_phase);
+        acc_phase ^= 1u;
+        tc_fence_after();
+    }
+    __device__ __forceinline__ void tmem_ld16(int lq, int col, float (&v)[16]) {
+        uint32_t r[16];
+        const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)col;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+    }
+};
+
+constexpr size_t kSmemBytesTC = (size_t)SmemMapTC::total_floats * 4 + 64;
+
+template <bool SR16, int RM, typename S>
+__global__ void __launch_bounds__(kThreads, 1) svad_fused_tc(TileArgs a, int ntiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SmemMapTC::total_floats * 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    GpuEnvTC<SR16> env{sm, bars, bars + 2, bars + 4, a.tape, (int)threadIdx.x, 0u, 0, -1, 0u, 0u, 0u};
+    int my_tiles = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + 2 + s)) : "memory");
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + 4)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const long total = (long)my_tiles * a.T * TapeTC<SR16>::nslab;
+        env.refill_upto(kStages - 1, total);
+    }
+    if (threadIdx.x < 32) {   // warp 0 owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    env.tmem = *tmem_slot;
+    run_cta_tc<SR16, RM, S>(env, a, (int)blockIdx.x, (int)gridDim.x, ntiles);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(env.tmem), "r"(kTmemCols) : "memory");
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host
@@ -123,8 +274,11 @@ static int fail(int code, const char* fmt, ...) {
 
 struct svad_engine {
     int device = 0, sms = 0, tile_rows = 0;
-    float* d_tape[2] = {nullptr, nullptr};    // 0: 16 kHz, 1: 8 kHz
+    float* d_tape[2] = {nullptr, nullptr};    // 0: 16 kHz, 1: 8 kHz   (fp32 CUDA-core kernel)
     float* d_consts[2] = {nullptr, nullptr};
+    float* d_tape_tc[2] = {nullptr, nullptr};  // tensor-core kernel
+    float* d_consts_tc[2] = {nullptr, nullptr};
+    int kernel = 0;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32
     int64_t launches = 0;
     // staging for the host-buffer entry points
     void *h_pin = nullptr, *d_buf = nullptr;
@@ -147,8 +301,9 @@ extern "C" int svad_engine_create(const char* weights_path, int device, svad_eng
     TensorMap tm;
     std::string err;
     if (!read_container(weights_path, tm, err)) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
-    PackedBranch pb[2];
+    PackedBranch pb[2], pbt[2];
     if (!pack_branch<true>(tm, pb[0], err) || !pack_branch<false>(tm, pb[1], err)) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
+    if (!pack_branch_tc<true>(tm, pbt[0], err) || !pack_branch_tc<false>(tm, pbt[1], err)) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -163,6 +318,10 @@ extern "C" int svad_engine_create(const char* weights_path, int device, svad_eng
         CUDA_TRY(cudaMalloc(&e->d_consts[b], pb[b].consts.size() * 4));
         CUDA_TRY(cudaMemcpy(e->d_tape[b], pb[b].tape.data(), pb[b].tape.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_consts[b], pb[b].consts.data(), pb[b].consts.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&e->d_tape_tc[b], pbt[b].tape.size() * 4));
+        CUDA_TRY(cudaMalloc(&e->d_consts_tc[b], pbt[b].consts.size() * 4));
+        CUDA_TRY(cudaMemcpy(e->d_tape_tc[b], pbt[b].tape.data(), pbt[b].tape.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(e->d_consts_tc[b], pbt[b].consts.data(), pbt[b].consts.size() * 4, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_copy, cudaStreamNonBlocking));
@@ -174,7 +333,7 @@ extern "C" int svad_engine_create(const char* weights_path, int device, svad_eng
 extern "C" void svad_engine_destroy(svad_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    for (int b = 0; b < 2; b++) { cudaFree(e->d_tape[b]); cudaFree(e->d_consts[b]); }
+    for (int b = 0; b < 2; b++) { cudaFree(e->d_tape[b]); cudaFree(e->d_consts[b]); cudaFree(e->d_tape_tc[b]); cudaFree(e->d_consts_tc[b]); }
     if (e->h_pin) cudaFreeHost(e->h_pin);
     if (e->d_buf) cudaFree(e->d_buf);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -186,6 +345,11 @@ extern "C" void svad_engine_destroy(svad_engine* e) {
 extern "C" int svad_engine_set_tile_rows(svad_engine* e, int rows) {
     if (!e || !(rows == 0 || (rows >= 4 && rows <= 8))) return fail(SVAD_EINVAL, "tile rows must be 0 or 4..8");
     e->tile_rows = rows;
+    return SVAD_OK;
+}
+extern "C" int svad_engine_set_kernel(svad_engine* e, int kernel) {
+    if (!e || (kernel != 0 && kernel != 1)) return fail(SVAD_EINVAL, "kernel must be 0 (fp32 CUDA cores) or 1 (tcgen05 split-TF32)");
+    e->kernel = kernel;
     return SVAD_OK;
 }
 extern "C" int svad_engine_sm_count(const svad_engine* e) { return e ? e->sms : 0; }
@@ -207,6 +371,22 @@ static int launch(svad_engine* e, const TileArgs& a, cudaStream_t st) {
     return SVAD_OK;
 }
 
+template <bool SR16, int RM, typename S>
+static int launch_tc(svad_engine* e, const TileArgs& a, cudaStream_t st) {
+    auto kern = svad_fused_tc<SR16, RM, S>;
+    static bool configured[16] = {};
+    if (!configured[e->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesTC));
+        configured[e->device & 15] = true;
+    }
+    const int ntiles = (a.B + 4 * RM - 1) / (4 * RM);
+    const int grid = ntiles < e->sms ? ntiles : e->sms;
+    kern<<<grid, kThreads, kSmemBytesTC, st>>>(a, ntiles);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return SVAD_OK;
+}
+
 // rows per thread that minimises (waves x rows): the FFMA work of a CTA step is proportional to RM.
 static int pick_rows(const svad_engine* e, int B) {
     if (e->tile_rows) return e->tile_rows;
@@ -223,6 +403,10 @@ static int pick_rows(const svad_engine* e, int B) {
 
 template <bool SR16, typename S>
 static int launch_rm(svad_engine* e, const TileArgs& a, cudaStream_t st) {
+    if (e->kernel == 1) {   // tensor-core kernel: MMA cost does not depend on the tile rows; only 7 and 8 are built
+        const int rm = e->tile_rows ? e->tile_rows : pick_rows(e, a.B);
+        return rm >= 8 ? launch_tc<SR16, 8, S>(e, a, st) : launch_tc<SR16, 7, S>(e, a, st);
+    }
     switch (pick_rows(e, a.B)) {
         case 4: return launch<SR16, 4, S>(e, a, st);
         case 5: return launch<SR16, 5, S>(e, a, st);
@@ -251,7 +435,9 @@ static int forward_impl(svad_engine* e, int sr, int B, int64_t L, int64_t ld, co
     a.audio = d_audio; a.ld = ld; a.L = L; a.B = B; a.T = T;
     a.state_in = d_state_in; a.ctx_in = d_ctx_in; a.ctx_ld = ctx_ld;
     a.state_out = d_state_out; a.ctx_out = d_ctx_out;
-    a.probs = d_probs; a.ldp = ldp; a.tape = e->d_tape[br]; a.consts = e->d_consts[br];
+    a.probs = d_probs; a.ldp = ldp;
+    a.tape = e->kernel == 1 ? e->d_tape_tc[br] : e->d_tape[br];
+    a.consts = e->kernel == 1 ? e->d_consts_tc[br] : e->d_consts[br];
     if (fmt == kI16) return sr == 16000 ? launch_rm<true, int16_t>(e, a, st) : launch_rm<false, int16_t>(e, a, st);
     return sr == 16000 ? launch_rm<true, float>(e, a, st) : launch_rm<false, float>(e, a, st);
 }

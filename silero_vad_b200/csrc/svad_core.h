@@ -76,6 +76,7 @@ struct Geo {
 // h    [128][32]
 // consts: b0[128] b1[64] b2[64] b3[128] bl[512] wout[128] bout[1] pad[3] win[256] twr[256] twi[256]
 struct SmemMap {
+    static constexpr bool kTC = false;
     static constexpr int mag = 0;
     static constexpr int mag_floats = 4 * 129 * kSlots;          // 16512
     static constexpr int e1 = mag;                               // [2][64][32]
@@ -96,9 +97,46 @@ struct SmemMap {
     static constexpr int stage_floats = kStageBytes / 4;
     static constexpr int total_floats = stage + kStages * stage_floats;
 };
+// Shared-memory map of the tensor-core kernel (svad_tc.h).  Same regions, but every buffer an MMA reads directly
+// (mag, e3, h and the "lo" staging tiles) is a stack of tcgen05 MN-major SWIZZLE_128B_BASE32B atoms: rows of 32
+// floats (one per channel k), 32-byte chunk index XORed with k & 3, 512-byte aligned bases, mag frames padded to
+// 132 rows so every frame starts on an atom boundary.  Weight stages hold K-major SWIZZLE_128B tiles (1 KB aligned).
+struct SmemMapTC {
+    static constexpr bool kTC = true;
+    static constexpr int mag_pitch = 132;                        // rows per frame
+    static constexpr int mag = 0;
+    static constexpr int mag_floats = 4 * mag_pitch * kSlots;    // 16896 floats = 132 x 512 B
+    static constexpr int e1 = mag;
+    static constexpr int e2 = e1 + 2 * 64 * kSlots;
+    static constexpr int e3 = e2 + 64 * kSlots;                  // 24576 B, atom aligned
+    static constexpr int e0 = mag + mag_floats;
+    static constexpr int zpitch = 257;
+    static constexpr int e0_floats = 129 * 128;                  // 66048 B >= Z planes (2*32*257) and e0 (4*128*32)
+    static constexpr int zre = e0;
+    static constexpr int zim = e0 + kSlots * zpitch;
+    static constexpr int lo0 = e0;                               // enc0 lo tiles [4][Kt][32] (after the STFT, before e0 is written)
+    static constexpr int lol = e0;                               // LSTM lo tiles [256][32]   (after enc1 has consumed e0)
+    static constexpr int h = e0 + e0_floats;                     // 133632 B, atom aligned
+    static constexpr int consts = h + kHid * kSlots;
+    static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_bout = 1024, c_win = 1028;
+    static constexpr int c_twr = c_win + 256, c_twi = c_twr + 256;
+    static constexpr int c_wnyq = c_twi + 256;                   // enc0 weights of the Nyquist bin: [3 taps][128]
+    static constexpr int consts_floats = c_wnyq + 384;
+    static constexpr int headp = consts + consts_floats;
+    static constexpr int stage = (headp + kSlots + 255) / 256 * 256;   // 1 KB aligned
+    static constexpr int stage_floats = kStageBytes / 4;
+    static constexpr int total_floats = stage + kStages * stage_floats;
+};
+static_assert(SmemMapTC::e0 % 128 == 0 && SmemMapTC::h % 128 == 0 && SmemMapTC::e3 % 128 == 0, "atom alignment");
+static_assert(SmemMapTC::e0_floats >= 2 * kSlots * SmemMapTC::zpitch, "Z planes");
+static_assert((size_t)SmemMapTC::total_floats * 4 + 256 <= 232448, "shared memory budget");
 static_assert(SmemMap::e0_floats >= 4 * 128 * kSlots, "e0 region too small");
 static_assert(SmemMap::e3 + 128 * kSlots <= SmemMap::mag + SmemMap::mag_floats, "e1/e2/e3 alias overflow");
 static_assert(SmemMap::stage % 4 == 0, "stage alignment");
+
+// tcgen05 MN-major SWIZZLE_128B_BASE32B row: 32-byte chunk (slot >> 3) XOR (row & 3)
+SVAD_HD int tc_slot(int slot, int row) { return (((slot >> 3) ^ (row & 3)) << 3) | (slot & 7); }
+SVAD_HD int tc_f4(int g, int row) { return (((g >> 1) ^ (row & 3)) << 1) | (g & 1); }   // physical float4 index of logical float4 g
 
 // ---------------------------------------------------------------- thread coordinates
 struct Tc {
@@ -273,14 +311,14 @@ SVAD_HD void stft_load(int tid, int fp, const S* audio, const float* ctx_in, lon
     }
 }
 
-template <bool SR16>
+template <bool SR16, class M = SmemMap>
 SVAD_HD void stft_pass_a(const Tc& tc, float* sm, const float (&xa)[Geo<SR16>::NQ], const float (&xb)[Geo<SR16>::NQ]) {
     using G = Geo<SR16>;
     constexpr int NQ = G::NQ;
     const int r = tc.tid & 15, hw = tc.tid >> 4;
-    const float* win = sm + SmemMap::consts + SmemMap::c_win + r;
-    const float* twr = sm + SmemMap::consts + SmemMap::c_twr + r;
-    const float* twi = sm + SmemMap::consts + SmemMap::c_twi + r;
+    const float* win = sm + M::consts + M::c_win + r;
+    const float* twr = sm + M::consts + M::c_twr + r;
+    const float* twi = sm + M::consts + M::c_twi + r;
     float zr[NQ], zi[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
@@ -290,10 +328,10 @@ SVAD_HD void stft_pass_a(const Tc& tc, float* sm, const float (&xa)[Geo<SR16>::N
     }
     fft_dif<NQ>(zr, zi);
     const int ia = zitem(hw, 0), ib = zitem(hw, 1);
-    float* za_re = sm + SmemMap::zre + ia * SmemMap::zpitch + r;
-    float* za_im = sm + SmemMap::zim + ia * SmemMap::zpitch + r;
-    float* zb_re = sm + SmemMap::zre + ib * SmemMap::zpitch + r;
-    float* zb_im = sm + SmemMap::zim + ib * SmemMap::zpitch + r;
+    float* za_re = sm + M::zre + ia * M::zpitch + r;
+    float* za_im = sm + M::zim + ia * M::zpitch + r;
+    float* zb_re = sm + M::zre + ib * M::zpitch + r;
+    float* zb_im = sm + M::zim + ib * M::zpitch + r;
 #pragma unroll
     for (int k = 0; k < NQ; k++) {
         const int pk = bitrev(k, ilog2(NQ)), pn = bitrev((NQ - k) % NQ, ilog2(NQ));
@@ -311,26 +349,27 @@ SVAD_HD void stft_pass_a(const Tc& tc, float* sm, const float (&xa)[Geo<SR16>::N
 // ---------------------------------------------------------------- STFT pass C
 // Thread (lane = exchange item -> slot, frame) takes k1 and runs the 16-point DFT over r;
 // bins k1 + NQ*k2, k2 < 8 (and N/2 for k1 = 0) of that (slot, frame) go to mag[frame][bin][slot].
-template <bool SR16>
+template <bool SR16, class M = SmemMap>
 SVAD_HD void stft_pass_c(const Tc& tc, float* sm, int hs, int fp, int k1) {
     using G = Geo<SR16>;
+    constexpr int pitch = M::kTC ? 132 : G::F;
     const int item = tc.lane;
     const int slot = 16 * hs + zitem_hw(item), f = 2 * fp + zitem_fr(item);
-    const float* zre = sm + SmemMap::zre + item * SmemMap::zpitch + k1 * 16;
-    const float* zim = sm + SmemMap::zim + item * SmemMap::zpitch + k1 * 16;
+    const float* zre = sm + M::zre + item * M::zpitch + k1 * 16;
+    const float* zim = sm + M::zim + item * M::zpitch + k1 * 16;
     float xr[16], xi[16];
 #pragma unroll
     for (int r = 0; r < 16; r++) { xr[r] = zre[r]; xi[r] = zim[r]; }
     fft_dif<16>(xr, xi);
-    float* mg = sm + SmemMap::mag + (f * G::F) * kSlots + slot;
+    float* mg = sm + M::mag + (f * pitch) * kSlots;
 #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) {
-        const int p = bitrev(k2, 4);
-        mg[(k1 + G::NQ * k2) * kSlots] = sqrtf(xr[p] * xr[p] + xi[p] * xi[p]);
+        const int p = bitrev(k2, 4), bin = k1 + G::NQ * k2;
+        mg[bin * kSlots + (M::kTC ? tc_slot(slot, bin) : slot)] = sqrtf(xr[p] * xr[p] + xi[p] * xi[p]);
     }
     if (k1 == 0) {
         const int p = bitrev(8, 4);
-        mg[(G::N / 2) * kSlots] = sqrtf(xr[p] * xr[p] + xi[p] * xi[p]);
+        mg[(G::N / 2) * kSlots + slot] = sqrtf(xr[p] * xr[p] + xi[p] * xi[p]);   // N/2 is a multiple of 4: identity swizzle
     }
 }
 
@@ -350,6 +389,11 @@ SVAD_HD void store8(float* row, int lm, int key, const float (&x)[8]) {
     f4 a{x[0], x[1], x[2], x[3]}, b{x[4], x[5], x[6], x[7]};
     *reinterpret_cast<f4*>(row + ((lm ^ key) << 2)) = a;
     *reinterpret_cast<f4*>(row + (((4 + lm) ^ key) << 2)) = b;
+}
+SVAD_HD void store8_tc(float* row, int lm, int ch, const float (&x)[8]) {
+    f4 a{x[0], x[1], x[2], x[3]}, b{x[4], x[5], x[6], x[7]};
+    *reinterpret_cast<f4*>(row + (tc_f4(lm, ch) << 2)) = a;
+    *reinterpret_cast<f4*>(row + (tc_f4(4 + lm, ch) << 2)) = b;
 }
 SVAD_HD float relu(float v) { return v > 0.0f ? v : 0.0f; }   // NaN -> 0 like fmaxf(v, 0)
 SVAD_HD float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -428,9 +472,9 @@ SVAD_HD void load8p(const float* row, int lm, int key, f2 (&x)[4]) {
     f4 b = *reinterpret_cast<const f4*>(row + (((4 + lm) ^ key) << 2));
     x[0] = f2{a.x, a.y}; x[1] = f2{a.z, a.w}; x[2] = f2{b.x, b.y}; x[3] = f2{b.z, b.w};
 }
-template <int RM>
+template <int RM, class M = SmemMap>
 SVAD_HD void enc1_init(const Tc& tc, const float* sm, Regs& rg) {
-    const float b = sm[SmemMap::consts + SmemMap::c_b1 + 8 * tc.warp + tc.ln];
+    const float b = sm[M::consts + M::c_b1 + 8 * tc.warp + tc.ln];
 #pragma unroll
     for (int k = 0; k < 8; k++) rg.acc[k] = f2{b, b};
 }
@@ -449,10 +493,10 @@ SVAD_HD void enc1_fma(const f2 (&x)[4][4], const float (&w)[3], Regs& rg) {
         rg.acc[4 + ip] = ffma2_s(w[2], x[3][ip], rg.acc[4 + ip]);
     }
 }
-template <int RM>
+template <int RM, class M = SmemMap>
 SVAD_HD void enc1_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int c0, int c1) {
     const float* wp = slab + 8 * tc.warp + tc.ln;
-    const float* e0 = sm + SmemMap::e0;
+    const float* e0 = sm + M::e0;
     f2 xa[4][4], xb[4][4];
     float wa[3], wb[3];
     enc1_fetch(tc, e0, wp, c0, xa, wa);
@@ -464,7 +508,7 @@ SVAD_HD void enc1_slab(const Tc& tc, const float* sm, const float* slab, Regs& r
         enc1_fma(xb, wb, rg);
     }
 }
-template <int RM>
+template <int RM, class M = SmemMap>
 SVAD_HD void enc1_store(const Tc& tc, float* sm, const Regs& rg) {
     const int o = 8 * tc.warp + tc.ln;
 #pragma unroll
@@ -475,24 +519,24 @@ SVAD_HD void enc1_store(const Tc& tc, float* sm, const Regs& rg) {
             v[2 * ip] = (2 * ip < RM) ? relu(rg.acc[t * 4 + ip].x) : 0.0f;
             v[2 * ip + 1] = (2 * ip + 1 < RM) ? relu(rg.acc[t * 4 + ip].y) : 0.0f;
         }
-        store8(sm + SmemMap::e1 + (t * 64 + o) * kSlots, tc.lm, key_lo(o), v);
+        store8(sm + M::e1 + (t * 64 + o) * kSlots, tc.lm, key_lo(o), v);
     }
 }
 
 // ---------------------------------------------------------------- enc2: 64 -> 64, stride 2, T 2 -> 1 (taps 1,2 live)
 // slab = W2p[c][jj][64], jj=0 <-> tap 1 (frame 0), jj=1 <-> tap 2 (frame 1); one slab, 64 channels.  Row pairs.
-template <int RM>
+template <int RM, class M = SmemMap>
 SVAD_HD void enc2_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
     const int o = 8 * tc.warp + tc.ln;
-    const float b = sm[SmemMap::consts + SmemMap::c_b2 + o];
+    const float b = sm[M::consts + M::c_b2 + o];
     f2 acc[4];
 #pragma unroll
     for (int ip = 0; ip < 4; ip++) acc[ip] = f2{b, b};
 #pragma unroll 4
     for (int c = 0; c < 64; c++) {
         f2 x0[4], x1[4];
-        load8p(sm + SmemMap::e1 + c * kSlots, tc.lm, key_lo(c), x0);
-        load8p(sm + SmemMap::e1 + (64 + c) * kSlots, tc.lm, key_lo(c), x1);
+        load8p(sm + M::e1 + c * kSlots, tc.lm, key_lo(c), x0);
+        load8p(sm + M::e1 + (64 + c) * kSlots, tc.lm, key_lo(c), x1);
         const float w0 = slab[c * 128 + o], w1 = slab[c * 128 + 64 + o];
 #pragma unroll
         for (int ip = 0; ip < 4; ip++) { acc[ip] = ffma2_s(w0, x0[ip], acc[ip]); acc[ip] = ffma2_s(w1, x1[ip], acc[ip]); }
@@ -503,23 +547,23 @@ SVAD_HD void enc2_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
         v[2 * ip] = (2 * ip < RM) ? relu(acc[ip].x) : 0.0f;
         v[2 * ip + 1] = (2 * ip + 1 < RM) ? relu(acc[ip].y) : 0.0f;
     }
-    store8(sm + SmemMap::e2 + o * kSlots, tc.lm, key_lo(o), v);
+    store8(sm + M::e2 + o * kSlots, tc.lm, key_lo(o), v);
     (void)rg;
 }
 
 // ---------------------------------------------------------------- enc3: 64 -> 128, T 1 -> 1 (tap 1 live)
 // slab = W3p[c][128]; cols 16*warp + 2*ln + u (column pairs).
-template <int RM>
+template <int RM, class M = SmemMap>
 SVAD_HD void enc3_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
     const int oc = 16 * tc.warp + 2 * tc.ln;
-    const f2 b3 = *reinterpret_cast<const f2*>(sm + SmemMap::consts + SmemMap::c_b3 + oc);
+    const f2 b3 = *reinterpret_cast<const f2*>(sm + M::consts + M::c_b3 + oc);
     f2 acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = b3;
 #pragma unroll 4
     for (int c = 0; c < 64; c++) {
         float x[8];
-        load8(sm + SmemMap::e2 + c * kSlots, tc.lm, key_lo(c), x);
+        load8(sm + M::e2 + c * kSlots, tc.lm, key_lo(c), x);
         const f2 w = *reinterpret_cast<const f2*>(slab + c * 128 + oc);
 #pragma unroll
         for (int i = 0; i < RM; i++) acc[i] = ffma2_s(x[i], w, acc[i]);
@@ -527,8 +571,13 @@ SVAD_HD void enc3_all(const Tc& tc, float* sm, const float* slab, Regs& rg) {
     float v0[8], v1[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { v0[i] = (i < RM) ? relu(acc[i].x) : 0.0f; v1[i] = (i < RM) ? relu(acc[i].y) : 0.0f; }
-    store8(sm + SmemMap::e3 + oc * kSlots, tc.lm, key_hi(oc), v0);
-    store8(sm + SmemMap::e3 + (oc + 1) * kSlots, tc.lm, key_hi(oc), v1);
+    if constexpr (M::kTC) {   // e3 is read by the LSTM MMAs: tcgen05 atom rows
+        store8_tc(sm + M::e3 + oc * kSlots, tc.lm, oc, v0);
+        store8_tc(sm + M::e3 + (oc + 1) * kSlots, tc.lm, oc + 1, v1);
+    } else {
+        store8(sm + M::e3 + oc * kSlots, tc.lm, key_hi(oc), v0);
+        store8(sm + M::e3 + (oc + 1) * kSlots, tc.lm, key_hi(oc), v1);
+    }
     (void)rg;
 }
 

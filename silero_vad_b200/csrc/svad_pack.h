@@ -153,4 +153,92 @@ inline bool pack_branch(const TensorMap& tm, PackedBranch& out, std::string& err
     return true;
 }
 
+// ---------------------------------------------------------------- tensor-core tape (svad_tc.h)
+// enc0 and the LSTM run on tcgen05 (kind::tf32, M=128 weights x N=32 stream slots x K=8), split precision
+//   x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo,   hi = fp32 value as is (the tensor core TRUNCATES fp32 containers to
+// tf32: tools/umma_unit.cu), lo = v - trunc_tf32(v) (exact in fp32).  A weight slab is one [128 rows x 32 k] tile pair
+// {hi | lo} in the K-major SWIZZLE_128B canonical layout (row r at (r/8)*1024 + (r%8)*128 B, 16-byte chunk (k/4)^(r%8)):
+//   enc0  for kc < Kt/32, tap j < 3 : rows o < 128, k = bins kc*32..+32 of W0[o][bin][j]     (Kt = 128 / 64)
+//         (the Nyquist bin F-1 is added on the CUDA cores from consts c_wnyq, a rank-1 update)
+//   enc1-3  as in Tape<> (CUDA-core layers)
+//   lstm  for kc < 8, gate block m < 4 : rows j < 128 (hidden unit), k = kc*32..+32 of [W_ih ; W_hh][m*128 + j][k]
+template <bool SR16>
+struct TapeTC {
+    using G = Geo<SR16>;
+    static constexpr int Kt = G::F - 1;                  // 128 / 64 bins on the tensor core
+    static constexpr int e0_nslab = (Kt / 32) * 3;       // 12 / 6
+    static constexpr int tile = 128 * 32;                // floats per tile
+    static constexpr int e0_off = 0;
+    static constexpr int e1_off = e0_off + e0_nslab * 2 * tile;
+    static constexpr int e2_off = e1_off + 128 * 192;
+    static constexpr int e3_off = e2_off + 64 * 128;
+    static constexpr int l_off = e3_off + 64 * 128;
+    static constexpr int total = l_off + 32 * 2 * tile;
+    static constexpr int nslab = e0_nslab + 4 + 1 + 1 + 32;
+    SVAD_HD static constexpr int slab_off(int i) {
+        if (i < e0_nslab) return e0_off + i * 2 * tile;
+        i -= e0_nslab;
+        if (i < 4) return e1_off + i * 32 * 192;
+        i -= 4;
+        if (i == 0) return e2_off;
+        if (i == 1) return e3_off;
+        i -= 2;
+        return l_off + i * 2 * tile;
+    }
+    SVAD_HD static constexpr int slab_len(int i) {
+        if (i < e0_nslab) return 2 * tile;
+        i -= e0_nslab;
+        if (i < 4) return 32 * 192;
+        i -= 4;
+        if (i < 2) return 64 * 128;
+        return 2 * tile;
+    }
+};
+
+inline float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
+
+// A[r][k] (r < 128, k < 32, row stride lda floats, k stride ldk) -> K-major SWIZZLE_128B tile pair {hi | lo}
+inline void pack_umma_a(const float* A, long lda, long ldk, float* dst) {
+    for (int r = 0; r < 128; r++)
+        for (int k = 0; k < 32; k++) {
+            const float v = A[r * lda + k * ldk];
+            const int pos = (r / 8) * 256 + (r % 8) * 32 + (((k / 4) ^ (r % 8)) * 4) + (k % 4);
+            dst[pos] = v;
+            dst[128 * 32 + pos] = v - trunc_tf32(v);
+        }
+}
+
+template <bool SR16>
+inline bool pack_branch_tc(const TensorMap& tm, PackedBranch& out, std::string& err) {
+    using G = Geo<SR16>;
+    using T = TapeTC<SR16>;
+    using T1 = Tape<SR16>;
+    PackedBranch v1;
+    if (!pack_branch<SR16>(tm, v1, err)) return false;
+    const std::string p = SR16 ? "_model." : "_model_8k.";
+    const float* w0 = tm.at(p + "encoder.0.reparam_conv.weight").data.data();   // [128][F][3]
+    const float* wih = tm.at(p + "decoder.rnn.weight_ih").data.data();          // [512][128]
+    const float* whh = tm.at(p + "decoder.rnn.weight_hh").data.data();
+    const float* bih = tm.at(p + "decoder.rnn.bias_ih").data.data();
+    const float* bhh = tm.at(p + "decoder.rnn.bias_hh").data.data();
+    out.tape.assign(T::total, 0.0f);
+    float* t = out.tape.data();
+    for (int kc = 0; kc < T::Kt / 32; kc++)
+        for (int j = 0; j < 3; j++)
+            pack_umma_a(w0 + (size_t)(kc * 32) * 3 + j, (long)G::F * 3, 3, t + T::e0_off + (kc * 3 + j) * 2 * T::tile);
+    memcpy(t + T::e1_off, v1.tape.data() + T1::e1_off, sizeof(float) * (T1::l_off - T1::e1_off));   // enc1..enc3 unchanged
+    for (int kc = 0; kc < 8; kc++)
+        for (int m = 0; m < 4; m++) {
+            const float* src = (kc < 4 ? wih : whh) + (size_t)(m * 128) * 128 + (kc & 3) * 32;
+            pack_umma_a(src, 128, 1, t + T::l_off + (kc * 4 + m) * 2 * T::tile);
+        }
+    out.consts.assign(SmemMapTC::consts_floats, 0.0f);
+    float* cs = out.consts.data();
+    memcpy(cs, v1.consts.data(), sizeof(float) * SmemMapTC::c_twr);             // b0..b3, (bl), wout, bout, window
+    for (int g = 0; g < 512; g++) cs[SmemMapTC::c_bl + g] = bih[g] + bhh[g];    // natural gate order here
+    for (int j = 0; j < 3; j++)
+        for (int o = 0; o < 128; o++) cs[SmemMapTC::c_wnyq + j * 128 + o] = w0[((size_t)o * G::F + (G::F - 1)) * 3 + j];
+    return true;
+}
+
 }  // namespace svad

@@ -13,7 +13,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../silero_vad_b200/csrc/svad_tile.h"
+#include "../../silero_vad_b200/csrc/svad_tc.h"
 
 using namespace svad;
 
@@ -75,6 +75,113 @@ void run(const TileArgs& a, int ntiles) {
     pthread_barrier_destroy(&sh.bar);
 }
 }  // namespace
+
+// ---------------------------------------------------------------- tensor-core schedule (svad_tc.h) on the CPU
+// tcgen05.mma is modelled as: D[128][32] (+)= trunc_tf32(A[128][8]) * trunc_tf32(B[8][32]) with A / B fetched through
+// the very swizzled shared-memory layouts the descriptors declare, fp32 accumulate.  Executed synchronously by the
+// issuing thread; TMEM is a plain array.
+namespace {
+struct SharedTC {
+    std::vector<float> smem;
+    std::vector<float> tmem;   // [128 lanes][256 columns]
+    pthread_barrier_t bar;
+    const float* tape;
+};
+inline float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
+
+template <bool SR16>
+struct EmuEnvTC {
+    SharedTC* sh;
+    int tid_;
+    long issued = 0, freed = -1;
+    int tid() const { return tid_; }
+    float* smem() { return sh->smem.data(); }
+    void sync() { pthread_barrier_wait(&sh->bar); }
+    void prefetch_l2(const void*) {}
+    void warp_sync() {}
+    void fence_async() {}
+    void tc_fence_before() {}
+    void tc_fence_after() {}
+    void issue(long it) {
+        const int idx = (int)(it % TapeTC<SR16>::nslab), stage = (int)(it % kStages);
+        memcpy(sh->smem.data() + SmemMapTC::stage + stage * SmemMapTC::stage_floats, sh->tape + TapeTC<SR16>::slab_off(idx),
+               sizeof(float) * TapeTC<SR16>::slab_len(idx));
+    }
+    const float* slab_wait(long it) { return sh->smem.data() + SmemMapTC::stage + (it % kStages) * SmemMapTC::stage_floats; }
+    void mark_free(long x) { freed = x; }
+    void free_upto(long x) { if (x > freed) freed = x; }
+    void refill_upto(long x, long total) { while (issued <= x && issued < total) issue(issued++); }
+    void mma(int col, const float* a_tile, int ks, const float* b_rows, bool acc) {
+        for (int r = 0; r < 128; r++) {
+            for (int n = 0; n < 32; n++) {
+                double s = 0.0;
+                for (int kk = 0; kk < 8; kk++) {
+                    const int k = ks * 8 + kk;
+                    const float av = a_tile[(r / 8) * 256 + (r % 8) * 32 + (((k / 4) ^ (r % 8)) * 4) + (k % 4)];
+                    const float bv = b_rows[kk * 32 + ((((n >> 3) ^ (kk & 3)) << 3) | (n & 7))];   // rows start at a multiple of 8: (row & 3) == (kk & 3)
+                    s += (double)tf32_trunc(av) * (double)tf32_trunc(bv);
+                }
+                float& d = sh->tmem[r * 256 + col + n];
+                d = (acc ? d : 0.0f) + (float)s;
+            }
+        }
+    }
+    void mma_slab_done(long) {}
+    void acc_commit() {}
+    void acc_wait() { pthread_barrier_wait(&sh->bar); }
+    void tmem_ld16(int lq, int col, float (&v)[16]) {
+        const int lane = 32 * lq + (tid_ & 31);
+        for (int i = 0; i < 16; i++) v[i] = sh->tmem[lane * 256 + col + i];
+    }
+};
+
+template <bool SR16, int RM, typename S>
+void run_tc(const TileArgs& a, int ntiles) {
+    SharedTC sh;
+    sh.smem.assign(SmemMapTC::total_floats, 0.0f);
+    sh.tmem.assign(128 * 256, 0.0f);
+    sh.tape = a.tape;
+    pthread_barrier_init(&sh.bar, nullptr, kThreads);
+    const long total = (long)ntiles * a.T * TapeTC<SR16>::nslab;
+    long pre = 0;
+    {
+        EmuEnvTC<SR16> e0{&sh, 0};
+        for (long i = 0; i < kStages && i < total; i++) { e0.issue(i); pre = i + 1; }
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < kThreads; t++)
+        th.emplace_back([&, t] {
+            EmuEnvTC<SR16> env{&sh, t};
+            env.issued = pre;
+            run_cta_tc<SR16, RM, S>(env, a, 0, 1, ntiles);
+        });
+    for (auto& x : th) x.join();
+    pthread_barrier_destroy(&sh.bar);
+}
+}  // namespace
+
+extern "C" int svad_emu_forward_tc(const char* weights, int sr, int rm, int B, long L, const void* audio, int pcm16,
+                                   const float* state_in, const float* ctx_in, float* state_out, float* ctx_out, float* probs) {
+    TensorMap tm;
+    std::string err;
+    if (!read_container(weights, tm, err)) return -1;
+    PackedBranch pb;
+    const bool sr16 = sr == 16000;
+    if (!(sr16 ? pack_branch_tc<true>(tm, pb, err) : pack_branch_tc<false>(tm, pb, err))) return -2;
+    const int n = sr16 ? 512 : 256;
+    TileArgs a{};
+    a.audio = audio; a.ld = L; a.L = L; a.B = B; a.T = (L + n - 1) / n;
+    a.state_in = state_in; a.ctx_in = ctx_in; a.ctx_ld = sr16 ? 64 : 32; a.state_out = state_out; a.ctx_out = ctx_out;
+    a.probs = probs; a.ldp = a.T; a.tape = pb.tape.data(); a.consts = pb.consts.data();
+    const int bt = 4 * rm, ntiles = (B + bt - 1) / bt;
+    if (pcm16) return -4;
+    if (sr16 && rm == 8) run_tc<true, 8, float>(a, ntiles);
+    else if (sr16 && rm == 7) run_tc<true, 7, float>(a, ntiles);
+    else if (!sr16 && rm == 8) run_tc<false, 8, float>(a, ntiles);
+    else if (!sr16 && rm == 7) run_tc<false, 7, float>(a, ntiles);
+    else return -3;
+    return 0;
+}
 
 extern "C" int svad_emu_forward(const char* weights, int sr, int rm, int B, long L, const void* audio, int pcm16, const float* state_in,
                                 const float* ctx_in, float* state_out, float* ctx_out, float* probs) {
