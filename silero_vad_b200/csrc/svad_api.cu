@@ -117,22 +117,28 @@ constexpr uint32_t kTmemCols = 256;
 template <bool SR16>
 struct GpuEnvTC {
     float* sm;
-    uint64_t* full;    // [kStages] slab landed (TMA tx)
-    uint64_t* mdone;   // [kStages] MMAs that read the stage have completed (tcgen05.commit)
+    uint64_t* full;    // [kTcStages] slab landed (TMA tx)
+    uint64_t* mdone;   // [kTcStages] MMAs that read the stage have completed (tcgen05.commit)
     uint64_t* accb;    // layer accumulators complete
     const float* tape;
     int tid_;
     uint32_t tmem;
-    long issued, freed;
-    uint32_t mcnt0, mcnt1, acc_phase;
+    // warp-0 bookkeeping (identical in all its lanes): next slab to issue / last slab known consumed, their position in
+    // the per-step schedule, parity bits of the mdone barriers, parity of the accumulator barrier
+    int issued, issued_idx, freed, freed_idx;
+    uint32_t mpar, acc_phase;
     __device__ __forceinline__ int tid() const { return tid_; }
     __device__ __forceinline__ float* smem() { return sm; }
     __device__ __forceinline__ void sync() { __syncthreads(); }
-    __device__ __forceinline__ void warp_sync() { __syncwarp(); }
     __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
     __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
     __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
     __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+    __device__ __forceinline__ static bool elect() {   // one lane of a fully converged warp
+        uint32_t pred;
+        asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+        return pred != 0;
+    }
     __device__ __forceinline__ static void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile(
             "{\n"
@@ -146,8 +152,8 @@ struct GpuEnvTC {
             "r"(parity)
             : "memory");
     }
-    __device__ __forceinline__ void issue(long it) {
-        const int idx = (int)(it % TapeTC<SR16>::nslab), stage = (int)(it % kStages);
+    __device__ __forceinline__ void issue(int it, int idx) {   // one lane
+        const int stage = it & (kTcStages - 1);
         const uint32_t bytes = (uint32_t)TapeTC<SR16>::slab_len(idx) * 4u;
         const uint32_t bar = smem_u32(full + stage);
         const uint32_t dst = smem_u32(sm + SmemMapTC::stage + stage * SmemMapTC::stage_floats);
@@ -157,46 +163,61 @@ struct GpuEnvTC {
                      "l"(src), "r"(bytes), "r"(bar)
                      : "memory");
     }
-    __device__ __forceinline__ const float* slab_wait(long it) {
-        const int stage = (int)(it % kStages);
-        mbar_wait(smem_u32(full + stage), (uint32_t)((it / kStages) & 1));
+    __device__ __forceinline__ const float* slab_wait(int it) {
+        const int stage = it & (kTcStages - 1);
+        mbar_wait(smem_u32(full + stage), (uint32_t)((it >> 2) & 1));
         return sm + SmemMapTC::stage + stage * SmemMapTC::stage_floats;
     }
-    __device__ __forceinline__ static bool is_mma_slab(long it) {
-        const int idx = (int)(it % TapeTC<SR16>::nslab);
-        return idx < TapeTC<SR16>::e0_nslab || idx >= TapeTC<SR16>::e0_nslab + 6;
+    __device__ __forceinline__ void advance_freed() {
+        freed++;
+        if (++freed_idx == TapeTC<SR16>::nslab) freed_idx = 0;
     }
-    __device__ __forceinline__ void mark_free(long x) { freed = x; }
-    __device__ __forceinline__ void free_upto(long x) {
-        for (long y = freed + 1; y <= x; y++) {
-            if (is_mma_slab(y)) {
-                if (y & 1) { mbar_wait(smem_u32(mdone + 1), mcnt1 & 1); mcnt1++; }
-                else { mbar_wait(smem_u32(mdone), mcnt0 & 1); mcnt0++; }
+    __device__ __forceinline__ void mark_free(int x) { advance_freed(); (void)x; }   // in order: x == freed + 1
+    __device__ __forceinline__ void free_upto(int x) {
+        while (freed < x) {
+            advance_freed();
+            if (TapeTC<SR16>::is_mma(freed_idx)) {
+                const int st = freed & (kTcStages - 1);
+                mbar_wait(smem_u32(mdone + st), (mpar >> st) & 1u);
+                mpar ^= 1u << st;
             }
         }
-        if (x > freed) freed = x;
     }
-    __device__ __forceinline__ void refill_upto(long x, long total) {
-        while (issued <= x && issued < total) { issue(issued); issued++; }
+    __device__ __forceinline__ void refill_upto(int x, int total) {
+        while (issued <= x && issued < total) {
+            if (elect()) issue(issued, issued_idx);
+            issued++;
+            if (++issued_idx == TapeTC<SR16>::nslab) issued_idx = 0;
+        }
     }
-    __device__ __forceinline__ void mma(int col, const float* a_tile, int ks, const float* b_rows, bool acc) {
-        const uint64_t ad = umma_desc(smem_u32(a_tile) + ks * 32, 16, 1024, 2);
-        const uint64_t bd = umma_desc(smem_u32(b_rows), 4096, 512, 1);
+    // descriptors: low word carries the address; a k-step advances A by 32 B and B by 8 rows = 1024 B
+    __device__ __forceinline__ uint64_t mma_a(const float* tile) const { return umma_desc(smem_u32(tile), 16, 1024, 2); }
+    // B: N atoms of 32 slots (consecutive frames for enc0) at stride lbo_bytes, 4-row k groups 512 B apart
+    __device__ __forceinline__ uint64_t mma_b(const float* rows, int lbo_bytes) const { return umma_desc(smem_u32(rows), (uint32_t)lbo_bytes, 512, 1); }
+    __device__ __forceinline__ void mma(int col, uint64_t ad, uint64_t bd, int ks, bool acc, int ncols) {
+        const uint64_t a2 = ad + (uint64_t)(ks * 2), b2 = bd + (uint64_t)(ks * 64);
         const uint32_t accf = acc ? 1u : 0u;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "setp.ne.b32 p, %4, 0;\n"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-            "}\n" ::"r"(tmem + (uint32_t)col),
-            "l"(ad), "l"(bd), "r"(kIdescTf32), "r"(accf)
-            : "memory");
+        const uint32_t idesc = (kIdescTf32 & ~(0x3Fu << 17)) | ((uint32_t)(ncols >> 3) << 17);
+        if (elect())
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.ne.b32 p, %4, 0;\n"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+                "}\n" ::"r"(tmem + (uint32_t)col),
+                "l"(a2), "l"(b2), "r"(idesc), "r"(accf)
+                : "memory");
     }
-    __device__ __forceinline__ void mma_slab_done(long it) {
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mdone + (it % kStages))) : "memory");
+    __device__ __forceinline__ void mma_slab_done(int it) {
+        if (elect())
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mdone + (it & (kTcStages - 1)))) : "memory");
+    }
+    __device__ __forceinline__ void slab_skip(int it) {   // an MMA warp that does not read this slab still releases it
+        if (elect()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mdone + (it & (kTcStages - 1)))) : "memory");
     }
     __device__ __forceinline__ void acc_commit() {
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(accb)) : "memory");
+        if (elect())
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(accb)) : "memory");
     }
     __device__ __forceinline__ void acc_wait() {
         mbar_wait(smem_u32(accb), acc_phase);
@@ -217,27 +238,30 @@ struct GpuEnvTC {
     }
 };
 
-constexpr size_t kSmemBytesTC = (size_t)SmemMapTC::total_floats * 4 + 64;
+constexpr size_t kSmemBytesTC = (size_t)SmemMapTC::total_floats * 4 + 128;
 
 template <bool SR16, int RM, typename S>
 __global__ void __launch_bounds__(kThreads, 1) svad_fused_tc(TileArgs a, int ntiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SmemMapTC::total_floats * 4);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    GpuEnvTC<SR16> env{sm, bars, bars + 2, bars + 4, a.tape, (int)threadIdx.x, 0u, 0, -1, 0u, 0u, 0u};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2);
+    GpuEnvTC<SR16> env{sm, bars, bars + kTcStages, bars + 2 * kTcStages, a.tape, (int)threadIdx.x, 0u, 0, 0, -1, -1, 0u, 0u};
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + 2 + s)) : "memory");
+        for (int s = 0; s < kTcStages; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)) : "memory");                 // full: TMA
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(bars + kTcStages + s)) : "memory");     // consumed: 4 MMA warps
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + 4)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(bars + 2 * kTcStages)) : "memory");         // accumulators: 4 MMA warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const long total = (long)my_tiles * a.T * TapeTC<SR16>::nslab;
-        env.refill_upto(kStages - 1, total);
+    }
+    __syncthreads();
+    if ((threadIdx.x >> 5) == kRingWarp) {   // the ring warp primes the weight ring
+        const int total = (int)((long)my_tiles * a.T * TapeTC<SR16>::nslab);
+        env.refill_upto(kTcStages - 1, total);
     }
     if (threadIdx.x < 32) {   // warp 0 owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
@@ -279,6 +303,7 @@ struct svad_engine {
     float* d_tape_tc[2] = {nullptr, nullptr};  // tensor-core kernel
     float* d_consts_tc[2] = {nullptr, nullptr};
     int kernel = 0;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32
+    long long* dbg = nullptr;
     int64_t launches = 0;
     // staging for the host-buffer entry points
     void *h_pin = nullptr, *d_buf = nullptr;
@@ -352,6 +377,12 @@ extern "C" int svad_engine_set_kernel(svad_engine* e, int kernel) {
     e->kernel = kernel;
     return SVAD_OK;
 }
+// profiling hook (not part of the public header): device buffer of 16 int64 clock stamps written by CTA 0
+extern "C" int svad_engine_set_debug_buffer(svad_engine* e, long long* d_buf) {
+    if (!e) return SVAD_EINVAL;
+    e->dbg = d_buf;
+    return SVAD_OK;
+}
 extern "C" int svad_engine_sm_count(const svad_engine* e) { return e ? e->sms : 0; }
 extern "C" int64_t svad_engine_launch_count(const svad_engine* e) { return e ? e->launches : 0; }
 
@@ -404,6 +435,7 @@ static int pick_rows(const svad_engine* e, int B) {
 template <bool SR16, typename S>
 static int launch_rm(svad_engine* e, const TileArgs& a, cudaStream_t st) {
     if (e->kernel == 1) {   // tensor-core kernel: MMA cost does not depend on the tile rows; only 7 and 8 are built
+        if (a.T > 4000000) return fail(SVAD_EINVAL, "tensor-core kernel: at most 4e6 chunks per call (feed long streams in pieces)");
         const int rm = e->tile_rows ? e->tile_rows : pick_rows(e, a.B);
         return rm >= 8 ? launch_tc<SR16, 8, S>(e, a, st) : launch_tc<SR16, 7, S>(e, a, st);
     }
@@ -435,7 +467,7 @@ static int forward_impl(svad_engine* e, int sr, int B, int64_t L, int64_t ld, co
     a.audio = d_audio; a.ld = ld; a.L = L; a.B = B; a.T = T;
     a.state_in = d_state_in; a.ctx_in = d_ctx_in; a.ctx_ld = ctx_ld;
     a.state_out = d_state_out; a.ctx_out = d_ctx_out;
-    a.probs = d_probs; a.ldp = ldp;
+    a.probs = d_probs; a.ldp = ldp; a.dbg = e->dbg;
     a.tape = e->kernel == 1 ? e->d_tape_tc[br] : e->d_tape[br];
     a.consts = e->kernel == 1 ? e->d_consts_tc[br] : e->d_consts[br];
     if (fmt == kI16) return sr == 16000 ? launch_rm<true, int16_t>(e, a, st) : launch_rm<false, int16_t>(e, a, st);

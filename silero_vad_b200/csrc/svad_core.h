@@ -34,6 +34,8 @@ constexpr int kHid = 128;
 constexpr int kGates = 512;
 constexpr int kStageBytes = 32768;  // one weight-tape slab buffer
 constexpr int kStages = 2;
+constexpr int kTcStageBytes = 16384;  // tensor-core kernel: 4 x 16 KB stages, up to 3-4 TMA copies in flight
+constexpr int kTcStages = 4;
 
 #if defined(__CUDACC__)
 using f4 = float4;
@@ -124,8 +126,8 @@ struct SmemMapTC {
     static constexpr int consts_floats = c_wnyq + 384;
     static constexpr int headp = consts + consts_floats;
     static constexpr int stage = (headp + kSlots + 255) / 256 * 256;   // 1 KB aligned
-    static constexpr int stage_floats = kStageBytes / 4;
-    static constexpr int total_floats = stage + kStages * stage_floats;
+    static constexpr int stage_floats = kTcStageBytes / 4;
+    static constexpr int total_floats = stage + kTcStages * stage_floats;
 };
 static_assert(SmemMapTC::e0 % 128 == 0 && SmemMapTC::h % 128 == 0 && SmemMapTC::e3 % 128 == 0, "atom alignment");
 static_assert(SmemMapTC::e0_floats >= 2 * kSlots * SmemMapTC::zpitch, "Z planes");

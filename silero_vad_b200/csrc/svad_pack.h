@@ -158,7 +158,7 @@ inline bool pack_branch(const TensorMap& tm, PackedBranch& out, std::string& err
 //   x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo,   hi = fp32 value as is (the tensor core TRUNCATES fp32 containers to
 // tf32: tools/umma_unit.cu), lo = v - trunc_tf32(v) (exact in fp32).  A weight slab is one [128 rows x 32 k] tile pair
 // {hi | lo} in the K-major SWIZZLE_128B canonical layout (row r at (r/8)*1024 + (r%8)*128 B, 16-byte chunk (k/4)^(r%8)):
-//   enc0  for kc < Kt/32, tap j < 3 : rows o < 128, k = bins kc*32..+32 of W0[o][bin][j]     (Kt = 128 / 64)
+//   enc0  for kc < Kt/32, tap j in (1, 0, 2) : rows o < 128, k = bins kc*32..+32 of W0[o][bin][j]     (Kt = 128 / 64)
 //         (the Nyquist bin F-1 is added on the CUDA cores from consts c_wnyq, a rank-1 update)
 //   enc1-3  as in Tape<> (CUDA-core layers)
 //   lstm  for kc < 8, gate block m < 4 : rows j < 128 (hidden unit), k = kc*32..+32 of [W_ih ; W_hh][m*128 + j][k]
@@ -166,32 +166,36 @@ template <bool SR16>
 struct TapeTC {
     using G = Geo<SR16>;
     static constexpr int Kt = G::F - 1;                  // 128 / 64 bins on the tensor core
-    static constexpr int e0_nslab = (Kt / 32) * 3;       // 12 / 6
-    static constexpr int tile = 128 * 32;                // floats per tile
+    static constexpr int tile = 128 * 32;                // floats per [128 x 32] tile = one 16 KB slab
+    static constexpr int e0_nslab = (Kt / 32) * 3 * 2;   // (kc, tap) x {hi, lo}: 24 / 12
+    static constexpr int e1_nslab = 8;                   // 16 channels x 192 floats
+    static constexpr int e2_nslab = 2, e3_nslab = 2;     // 32 channels x 128 floats
+    static constexpr int l_nslab = 64;                   // (kc, gate block) x {hi, lo}
     static constexpr int e0_off = 0;
-    static constexpr int e1_off = e0_off + e0_nslab * 2 * tile;
+    static constexpr int e1_off = e0_off + e0_nslab * tile;
     static constexpr int e2_off = e1_off + 128 * 192;
     static constexpr int e3_off = e2_off + 64 * 128;
     static constexpr int l_off = e3_off + 64 * 128;
-    static constexpr int total = l_off + 32 * 2 * tile;
-    static constexpr int nslab = e0_nslab + 4 + 1 + 1 + 32;
+    static constexpr int total = l_off + l_nslab * tile;
+    static constexpr int nsimt = e1_nslab + e2_nslab + e3_nslab;
+    static constexpr int nslab = e0_nslab + nsimt + l_nslab;
+    SVAD_HD static constexpr bool is_mma(int i) { return i < e0_nslab || i >= e0_nslab + nsimt; }
     SVAD_HD static constexpr int slab_off(int i) {
-        if (i < e0_nslab) return e0_off + i * 2 * tile;
+        if (i < e0_nslab) return e0_off + i * tile;
         i -= e0_nslab;
-        if (i < 4) return e1_off + i * 32 * 192;
-        i -= 4;
-        if (i == 0) return e2_off;
-        if (i == 1) return e3_off;
-        i -= 2;
-        return l_off + i * 2 * tile;
+        if (i < e1_nslab) return e1_off + i * 16 * 192;
+        i -= e1_nslab;
+        if (i < e2_nslab) return e2_off + i * 32 * 128;
+        i -= e2_nslab;
+        if (i < e3_nslab) return e3_off + i * 32 * 128;
+        i -= e3_nslab;
+        return l_off + i * tile;
     }
     SVAD_HD static constexpr int slab_len(int i) {
-        if (i < e0_nslab) return 2 * tile;
+        if (i < e0_nslab) return tile;
         i -= e0_nslab;
-        if (i < 4) return 32 * 192;
-        i -= 4;
-        if (i < 2) return 64 * 128;
-        return 2 * tile;
+        if (i < e1_nslab) return 16 * 192;
+        return tile;   // enc2 / enc3 halves and LSTM tiles are all 4096 floats
     }
 };
 
@@ -224,8 +228,10 @@ inline bool pack_branch_tc(const TensorMap& tm, PackedBranch& out, std::string& 
     out.tape.assign(T::total, 0.0f);
     float* t = out.tape.data();
     for (int kc = 0; kc < T::Kt / 32; kc++)
-        for (int j = 0; j < 3; j++)
-            pack_umma_a(w0 + (size_t)(kc * 32) * 3 + j, (long)G::F * 3, 3, t + T::e0_off + (kc * 3 + j) * 2 * T::tile);
+        for (int jo = 0; jo < 3; jo++) {   // tap order 1, 0, 2 (see svad_tc.h)
+            const int j = jo == 0 ? 1 : (jo == 1 ? 0 : 2);
+            pack_umma_a(w0 + (size_t)(kc * 32) * 3 + j, (long)G::F * 3, 3, t + T::e0_off + (kc * 3 + jo) * 2 * T::tile);   // {hi | lo} = 2 slabs
+        }
     memcpy(t + T::e1_off, v1.tape.data() + T1::e1_off, sizeof(float) * (T1::l_off - T1::e1_off));   // enc1..enc3 unchanged
     for (int kc = 0; kc < 8; kc++)
         for (int m = 0; m < 4; m++) {

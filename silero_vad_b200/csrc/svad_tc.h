@@ -19,14 +19,18 @@
 //   fence_async()                       make generic-proxy smem writes visible to the MMA (async proxy)
 //   tc_fence_before() / tc_fence_after()  order tcgen05.ld against later MMAs across a CTA barrier
 //   slab_wait(it)                       weight ring: wait until slab it has landed in its stage
-//   thread 0 only (it keeps `issued` / `freed` counters, so the calls are idempotent):
+//   warp 0 only, executed by all its lanes with identical (warp-uniform) bookkeeping so that descriptors and
+//   counters stay in uniform registers; the single-lane work (TMA issue, MMA, commit) is elected inside:
 //     mark_free(it)     slab it was consumed by the CUDA cores (a CTA barrier has passed)
 //     free_upto(it)     wait until the MMAs reading every slab <= it have completed
-//     refill_upto(it)   issue the TMA copies of all not yet issued slabs <= it (slab i reuses the stage of i-2)
+//     refill_upto(it)   issue the TMA copies of all not yet issued slabs <= it (slab i reuses the stage of i-4)
+//     mma_a(tile) / mma_b(rows)           descriptors; mma(col, adesc, ks, bdesc, ks, acc) issues one instruction
 #pragma once
 #include "svad_tile.h"
 
 namespace svad {
+
+constexpr int kRingWarp = 4;   // owns the weight ring (TMA issue, stage-free bookkeeping); warps 0-3 are the MMA warps
 
 SVAD_HD float lo_part(float v) {   // v - trunc_tf32(v), exact
 #if defined(__CUDA_ARCH__)
@@ -43,6 +47,71 @@ SVAD_HD void stage_lo(int tid, const float* src, float* dst, int nrows) {
         *reinterpret_cast<f4*>(dst + i * 4) = f4{lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w)};
     }
 }
+
+// enc2 / enc3 in slab form (the 16 KB ring holds 32 input channels per slab); accumulators live in rg.acc
+template <int RM, class M>
+SVAD_HD void enc2_slab_tc(const Tc& tc, float* sm, const float* slab, Regs& rg, int c0, bool first, bool last) {
+    const int o = 8 * tc.warp + tc.ln;
+    if (first) {
+        const float b = sm[M::consts + M::c_b2 + o];
+#pragma unroll
+        for (int ip = 0; ip < 4; ip++) rg.acc[ip] = f2{b, b};
+    }
+#pragma unroll 4
+    for (int cc = 0; cc < 32; cc++) {
+        const int c = c0 + cc;
+        f2 x0[4], x1[4];
+        load8p(sm + M::e1 + c * kSlots, tc.lm, key_lo(c), x0);
+        load8p(sm + M::e1 + (64 + c) * kSlots, tc.lm, key_lo(c), x1);
+        const float w0 = slab[cc * 128 + o], w1 = slab[cc * 128 + 64 + o];
+#pragma unroll
+        for (int ip = 0; ip < 4; ip++) { rg.acc[ip] = ffma2_s(w0, x0[ip], rg.acc[ip]); rg.acc[ip] = ffma2_s(w1, x1[ip], rg.acc[ip]); }
+    }
+    if (last) {
+        float v[8];
+#pragma unroll
+        for (int ip = 0; ip < 4; ip++) {
+            v[2 * ip] = (2 * ip < RM) ? relu(rg.acc[ip].x) : 0.0f;
+            v[2 * ip + 1] = (2 * ip + 1 < RM) ? relu(rg.acc[ip].y) : 0.0f;
+        }
+        store8(sm + M::e2 + o * kSlots, tc.lm, key_lo(o), v);
+    }
+}
+template <int RM, class M>
+SVAD_HD void enc3_slab_tc(const Tc& tc, float* sm, const float* slab, Regs& rg, int c0, bool first, bool last) {
+    const int oc = 16 * tc.warp + 2 * tc.ln;
+    if (first) {
+        const f2 b3 = *reinterpret_cast<const f2*>(sm + M::consts + M::c_b3 + oc);
+#pragma unroll
+        for (int i = 0; i < 8; i++) rg.acc[i] = b3;
+    }
+#pragma unroll 4
+    for (int cc = 0; cc < 32; cc++) {
+        const int c = c0 + cc;
+        float x[8];
+        load8(sm + M::e2 + c * kSlots, tc.lm, key_lo(c), x);
+        const f2 w = *reinterpret_cast<const f2*>(slab + cc * 128 + oc);
+#pragma unroll
+        for (int i = 0; i < RM; i++) rg.acc[i] = ffma2_s(x[i], w, rg.acc[i]);
+    }
+    if (last) {
+        float v0[8], v1[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { v0[i] = (i < RM) ? relu(rg.acc[i].x) : 0.0f; v1[i] = (i < RM) ? relu(rg.acc[i].y) : 0.0f; }
+        store8_tc(sm + M::e3 + oc * kSlots, tc.lm, oc, v0);
+        store8_tc(sm + M::e3 + (oc + 1) * kSlots, tc.lm, oc + 1, v1);
+    }
+}
+
+#if defined(__CUDA_ARCH__)
+#define SVAD_STAMP(k) do { if (a.dbg && first_tile == 0 && t == 2 && tc.tid == 0) a.dbg[k] = clock64(); } while (0)
+#define SVAD_CLK(v) const long long v = clock64()
+#define SVAD_ACC(k, d) do { if (a.dbg && first_tile == 0 && t == 2 && tc.tid == 0) a.dbg[k] += (d); } while (0)
+#else
+#define SVAD_STAMP(k) do { } while (0)
+#define SVAD_CLK(v) do { } while (0)
+#define SVAD_ACC(k, d) do { } while (0)
+#endif
 
 template <bool SR16, int RM, typename S, class Env>
 SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_stride, int ntiles) {
@@ -76,8 +145,8 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
     }
     int my_tiles = 0;
     for (int tile = first_tile; tile < ntiles; tile += tile_stride) my_tiles++;
-    const long total_slabs = (long)my_tiles * a.T * TP::nslab;
-    long it = 0;
+    const int total_slabs = (int)((long)my_tiles * a.T * TP::nslab);   // < 2^31 (checked on the host)
+    int it = 0;
     float cst[16];   // LSTM cell state of hidden unit `row` for slots 16*half .. +16
 
     for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
@@ -109,6 +178,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
 
         float xa[G::NQ], xb[G::NQ];
         for (long t = 0; t < a.T; t++) {
+            SVAD_STAMP(0);
             // ---------------- STFT (CUDA cores) -> mag rows in tcgen05 atom layout
             const bool fast = (t > 0) && ((t + 1) * G::n <= a.L);
             if (t + 1 < a.T) {
@@ -135,6 +205,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     for (int q = 0; q < G::NQ; q++) { xa[q] = na[q]; xb[q] = nb[q]; }
                 }
             }
+            SVAD_STAMP(1);
             // ---------------- enc0 on the tensor core
             // lo rows of mag[f][0..Kt) -> lo0[f][0..Kt)  (the Z planes there are dead now)
 #pragma unroll
@@ -142,38 +213,53 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
             env.fence_async();
             env.tc_fence_before();     // the previous step's tcgen05.ld of these TMEM columns are done
             env.sync();
-            if (tc.warp == 0) {
-                if (tc.lane == 0) {
-                    env.tc_fence_after();
+            SVAD_STAMP(2);
+            // Warps 0-3 are the MMA warps (each walks every slab: wait for it to land, use it or just release it, so the
+            // "stage consumed" barriers always collect 4 arrivals).  enc0: warp 0 issues; one instruction covers all frames a
+            // tap contributes to (N = 96 or 128: the frames are consecutive 32-column atoms of the B operand, LBO = frame pitch).
+            // Tap order in the tape is 1, 0, 2 so that the very first MMA (tap 1) overwrites all four frame blocks.
+            if (tc.warp < 4) {
+                env.tc_fence_after();
 #pragma unroll 1
-                    for (int s = 0; s < TP::e0_nslab; s++) {
-                        const long is = it + s;
-                        const int kc = s / 3, j = s % 3;
-                        const float* slab = env.slab_wait(is);
-#pragma unroll 1
-                        for (int tt = 0; tt < 4; tt++) {
-                            const int f = tt + j - 1;
-                            if (f < 0 || f > 3) continue;
-                            const float* bh = sm + M::mag + (f * M::mag_pitch + kc * 32) * kSlots;
-                            const float* bl = sm + M::lo0 + (f * Kt + kc * 32) * kSlots;
+                for (int s = 0; s < TP::e0_nslab; s++) {
+                    const int is = it + s;
+                    const int kc = s / 6, jo = (s >> 1) % 3, lo = s & 1;
+                    const int j = (jo == 0) ? 1 : (jo == 1 ? 0 : 2);
+                    SVAD_CLK(c0);
+                    const float* tile = env.slab_wait(is);
+                    SVAD_CLK(c1); SVAD_ACC(11, c1 - c0);
+                    if (tc.warp == 0) {
+                        const int f0 = (j == 2) ? 1 : 0, t0 = f0 + 1 - j, nf = (j == 1) ? 4 : 3;
+                        const auto ad = env.mma_a(tile);
+                        const auto bh = env.mma_b(sm + M::mag + (f0 * M::mag_pitch + kc * 32) * kSlots, M::mag_pitch * kSlots * 4);
+                        const auto bl = env.mma_b(sm + M::lo0 + (f0 * Kt + kc * 32) * kSlots, Kt * kSlots * 4);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ks++) {
-                                const bool first = (kc == 0) && (ks == 0) && (j == (tt == 0 ? 1 : 0));
-                                env.mma(tt * 32, slab, ks, bh + ks * 8 * kSlots, !first);
-                                env.mma(tt * 32, slab, ks, bl + ks * 8 * kSlots, true);
-                                env.mma(tt * 32, slab + TP::tile, ks, bh + ks * 8 * kSlots, true);
+                        for (int ks = 0; ks < 4; ks++) {
+                            if (!lo) {
+                                const bool first = (kc == 0) && (ks == 0) && (jo == 0);
+                                env.mma(t0 * 32, ad, bh, ks, !first, 32 * nf);   // w_hi * x_hi
+                                env.mma(t0 * 32, ad, bl, ks, true, 32 * nf);     // w_hi * x_lo
+                            } else {
+                                env.mma(t0 * 32, ad, bh, ks, true, 32 * nf);     // w_lo * x_hi
                             }
                         }
                         env.mma_slab_done(is);
-                        env.free_upto(is - 1);
-                        env.refill_upto(is + 1, total_slabs);
+                    } else {
+                        env.slab_skip(is);
                     }
-                    env.acc_commit();
                 }
-                env.warp_sync();
+                env.acc_commit();
+                SVAD_STAMP(3);
+            } else if (tc.warp == kRingWarp) {   // ring manager: as each slab is released, issue the next pending one
+#pragma unroll 1
+                for (int s = 0; s < TP::e0_nslab; s++) {
+                    env.free_upto(it + s);
+                    env.refill_upto(it + s + kTcStages, total_slabs);
+                }
             }
             it += TP::e0_nslab;
             env.acc_wait();
+            SVAD_STAMP(4);
             // epilogue: this thread owns channel `row`, frames 2*half, 2*half+1: + bias + Nyquist-bin rank-1 term, ReLU -> e0
             {
                 const float b0 = sm[M::consts + M::c_b0 + row];
@@ -202,65 +288,83 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
             }
             env.tc_fence_before();
             env.sync();
-            if (tc.tid == 0) {   // the stage of the last enc0 slab is free now
-                env.free_upto(it - 1);
-                env.refill_upto(it + 1, total_slabs);
-            }
+            SVAD_STAMP(5);
             // ---------------- enc1..enc3 on the CUDA cores (as in the fp32 kernel)
             enc1_init<RM, M>(tc, sm, rg);
 #pragma unroll 1
-            for (int s = 0; s < 4; s++, it++) {
+            for (int s = 0; s < TP::e1_nslab; s++, it++) {
                 const float* slab = env.slab_wait(it);
-                enc1_slab<RM, M>(tc, sm, slab, rg, s * 32, s * 32 + 32);
-                if (s == 3) enc1_store<RM, M>(tc, sm, rg);
+                enc1_slab<RM, M>(tc, sm, slab, rg, s * 16, s * 16 + 16);
+                if (s == TP::e1_nslab - 1) enc1_store<RM, M>(tc, sm, rg);
                 env.sync();
-                if (tc.tid == 0) { env.mark_free(it); env.refill_upto(it + 2, total_slabs); }
+                if (tc.warp == kRingWarp) { env.mark_free(it); env.refill_upto(it + kTcStages, total_slabs); }
             }
-            {
+#pragma unroll 1
+            for (int s = 0; s < 2; s++, it++) {
                 const float* slab = env.slab_wait(it);
-                enc2_all<RM, M>(tc, sm, slab, rg);
+                enc2_slab_tc<RM, M>(tc, sm, slab, rg, s * 32, s == 0, s == 1);
                 env.sync();
-                if (tc.tid == 0) { env.mark_free(it); env.refill_upto(it + 2, total_slabs); }
-                it++;
-                slab = env.slab_wait(it);
-                enc3_all<RM, M>(tc, sm, slab, rg);
-                // lo rows of h (carried from the previous step) can be staged before the barrier
-                stage_lo(tc.tid, sm + M::h, sm + M::lol + kHid * kSlots, kHid);
-                env.sync();
-                if (tc.tid == 0) { env.mark_free(it); env.refill_upto(it + 2, total_slabs); }
-                it++;
+                if (tc.warp == kRingWarp) { env.mark_free(it); env.refill_upto(it + kTcStages, total_slabs); }
             }
+#pragma unroll 1
+            for (int s = 0; s < 2; s++, it++) {
+                const float* slab = env.slab_wait(it);
+                enc3_slab_tc<RM, M>(tc, sm, slab, rg, s * 32, s == 0, s == 1);
+                if (s == 1) stage_lo(tc.tid, sm + M::h, sm + M::lol + kHid * kSlots, kHid);   // h is from the previous step
+                env.sync();
+                if (tc.warp == kRingWarp) { env.mark_free(it); env.refill_upto(it + kTcStages, total_slabs); }
+            }
+            SVAD_STAMP(6);
             // ---------------- LSTM on the tensor core: gates[m*128 + j][slot] = sum_k W[.][k] * [e3 ; h][k][slot]
             stage_lo(tc.tid, sm + M::e3, sm + M::lol, kHid);
             env.fence_async();
             env.sync();
-            if (tc.warp == 0) {
-                if (tc.lane == 0) {
-                    env.tc_fence_after();
+            SVAD_STAMP(7);
+            if (tc.warp < 4) {   // MMA warp m issues gate block m
+                env.tc_fence_after();
 #pragma unroll 1
-                    for (int s = 0; s < 32; s++) {
-                        const long is = it + s;
-                        const int kc = s >> 2, m = s & 3;
-                        const float* slab = env.slab_wait(is);
-                        const float* bh = (kc < 4) ? sm + M::e3 + kc * 32 * kSlots : sm + M::h + (kc - 4) * 32 * kSlots;
-                        const float* bl = sm + M::lol + kc * 32 * kSlots;
+                for (int s = 0; s < TP::l_nslab; s++) {
+                    const int is = it + s;
+                    const int kc = s >> 3, m = (s >> 1) & 3, lo = s & 1;
+                    SVAD_CLK(c0);
+                    const float* tile = env.slab_wait(is);
+                    SVAD_CLK(c1); SVAD_ACC(13, c1 - c0);
+                    if (m == tc.warp) {
+                        SVAD_CLK(d0);
+                        const auto ad = env.mma_a(tile);
+                        const auto bh = env.mma_b((kc < 4) ? sm + M::e3 + kc * 32 * kSlots : sm + M::h + (kc - 4) * 32 * kSlots, 4096);
+                        const auto bl = env.mma_b(sm + M::lol + kc * 32 * kSlots, 4096);
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
-                            const bool first = (kc == 0) && (ks == 0);
-                            env.mma(128 + m * 32, slab, ks, bh + ks * 8 * kSlots, !first);
-                            env.mma(128 + m * 32, slab, ks, bl + ks * 8 * kSlots, true);
-                            env.mma(128 + m * 32, slab + TP::tile, ks, bh + ks * 8 * kSlots, true);
+                            if (!lo) {
+                                const bool first = (kc == 0) && (ks == 0);
+                                env.mma(128 + m * 32, ad, bh, ks, !first, 32);
+                                env.mma(128 + m * 32, ad, bl, ks, true, 32);
+                            } else {
+                                env.mma(128 + m * 32, ad, bh, ks, true, 32);
+                            }
                         }
+                        SVAD_CLK(d1); SVAD_ACC(15, d1 - d0);
                         env.mma_slab_done(is);
-                        env.free_upto(is - 1);
-                        env.refill_upto(is + 1, total_slabs);
+                        SVAD_CLK(d2); SVAD_ACC(16, d2 - d1);
+                    } else {
+                        SVAD_CLK(d3);
+                        env.slab_skip(is);
+                        SVAD_CLK(d4); SVAD_ACC(17, d4 - d3);
                     }
-                    env.acc_commit();
                 }
-                env.warp_sync();
+                env.acc_commit();
+                SVAD_STAMP(8);
+            } else if (tc.warp == kRingWarp) {
+#pragma unroll 1
+                for (int s = 0; s < TP::l_nslab; s++) {
+                    env.free_upto(it + s);
+                    env.refill_upto(it + s + kTcStages, total_slabs);
+                }
             }
-            it += 32;
+            it += TP::l_nslab;
             env.acc_wait();
+            SVAD_STAMP(9);
             // epilogue: hidden unit `row`, slots 16*half..+16
             {
                 float gi[16], gf[16], gg[16], go[16];
@@ -285,10 +389,6 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
             }
             env.tc_fence_before();
             env.sync();
-            if (tc.tid == 0) {
-                env.free_upto(it - 1);
-                env.refill_upto(it + 1, total_slabs);
-            }
             if (tc.tid < kSlots) {
                 const int g = g0 + slot_to_local<RM>(tc.tid);
                 if (slot_valid<RM>(tc.tid) && g < a.B) {
@@ -303,6 +403,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 }
             }
             if (t + 1 < a.T) stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t + 1, ((t + 2) * G::n <= a.L), xa, xb);
+            SVAD_STAMP(10);
         }
         // ---- tile exit
         env.sync();

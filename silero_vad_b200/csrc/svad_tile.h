@@ -30,6 +30,7 @@ struct TileArgs {
     long ldp;
     const float* tape;      // weight tape (Tape<SR16>::total floats)
     const float* consts;    // SmemMap::consts_floats floats
+    long long* dbg;         // optional: per-phase clock64 stamps of CTA 0 (tensor-core kernel, profiling builds)
 };
 
 template <bool SR16, int RM, typename S, class Env>

@@ -7,6 +7,7 @@
 #include <sched.h>
 
 #include <atomic>
+#include <memory>
 
 #include <cstdlib>
 #include <string>
@@ -86,6 +87,8 @@ struct SharedTC {
     std::vector<float> tmem;   // [128 lanes][256 columns]
     pthread_barrier_t bar;
     const float* tape;
+    std::atomic<int> landed{0};                      // slabs copied into the ring so far ("full" barriers)
+    std::unique_ptr<std::atomic<int>[]> released;    // per slab: MMA-warp arrivals ("consumed" barriers, 4 expected)
 };
 inline float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 
@@ -93,32 +96,51 @@ template <bool SR16>
 struct EmuEnvTC {
     SharedTC* sh;
     int tid_;
-    long issued = 0, freed = -1;
+    int issued = 0, freed = -1;
     int tid() const { return tid_; }
     float* smem() { return sh->smem.data(); }
     void sync() { pthread_barrier_wait(&sh->bar); }
     void prefetch_l2(const void*) {}
-    void warp_sync() {}
     void fence_async() {}
     void tc_fence_before() {}
     void tc_fence_after() {}
-    void issue(long it) {
-        const int idx = (int)(it % TapeTC<SR16>::nslab), stage = (int)(it % kStages);
+    bool lane0() const { return (tid_ & 31) == 0; }
+    void issue(int it) {
+        const int idx = it % TapeTC<SR16>::nslab, stage = it % kTcStages;
         memcpy(sh->smem.data() + SmemMapTC::stage + stage * SmemMapTC::stage_floats, sh->tape + TapeTC<SR16>::slab_off(idx),
                sizeof(float) * TapeTC<SR16>::slab_len(idx));
     }
-    const float* slab_wait(long it) { return sh->smem.data() + SmemMapTC::stage + (it % kStages) * SmemMapTC::stage_floats; }
-    void mark_free(long x) { freed = x; }
-    void free_upto(long x) { if (x > freed) freed = x; }
-    void refill_upto(long x, long total) { while (issued <= x && issued < total) issue(issued++); }
-    void mma(int col, const float* a_tile, int ks, const float* b_rows, bool acc) {
+    const float* slab_wait(int it) {
+        while (sh->landed.load(std::memory_order_acquire) <= it) sched_yield();
+        return sh->smem.data() + SmemMapTC::stage + (it % kTcStages) * SmemMapTC::stage_floats;
+    }
+    void mark_free(int x) { freed = x; }
+    void free_upto(int x) {
+        for (int y = freed + 1; y <= x; y++)
+            if (TapeTC<SR16>::is_mma(y % TapeTC<SR16>::nslab))
+                while (sh->released[y].load(std::memory_order_acquire) < 4) sched_yield();
+        if (x > freed) freed = x;
+    }
+    void refill_upto(int x, int total) {
+        while (issued <= x && issued < total) {
+            if (lane0()) { issue(issued); sh->landed.store(issued + 1, std::memory_order_release); }
+            issued++;
+        }
+    }
+    struct BDesc { const float* rows; int lbo_floats; };
+    const float* mma_a(const float* tile) { return tile; }
+    BDesc mma_b(const float* rows, int lbo_bytes) { return BDesc{rows, lbo_bytes / 4}; }
+    void mma(int col, const float* a_tile, BDesc b, int ks, bool acc, int ncols) {
+        if (!lane0()) return;
         for (int r = 0; r < 128; r++) {
-            for (int n = 0; n < 32; n++) {
+            for (int n = 0; n < ncols; n++) {
+                const float* b_rows = b.rows + (n >> 5) * b.lbo_floats + ks * 8 * 32;   // N atom n/32 at stride LBO
+                const int nn = n & 31;
                 double s = 0.0;
                 for (int kk = 0; kk < 8; kk++) {
                     const int k = ks * 8 + kk;
                     const float av = a_tile[(r / 8) * 256 + (r % 8) * 32 + (((k / 4) ^ (r % 8)) * 4) + (k % 4)];
-                    const float bv = b_rows[kk * 32 + ((((n >> 3) ^ (kk & 3)) << 3) | (n & 7))];   // rows start at a multiple of 8: (row & 3) == (kk & 3)
+                    const float bv = b_rows[kk * 32 + ((((nn >> 3) ^ (kk & 3)) << 3) | (nn & 7))];   // rows start at a multiple of 8: (row & 3) == (kk & 3)
                     s += (double)tf32_trunc(av) * (double)tf32_trunc(bv);
                 }
                 float& d = sh->tmem[r * 256 + col + n];
@@ -126,7 +148,8 @@ struct EmuEnvTC {
             }
         }
     }
-    void mma_slab_done(long) {}
+    void mma_slab_done(int it) { if (lane0()) sh->released[it].fetch_add(1, std::memory_order_acq_rel); }
+    void slab_skip(int it) { if (lane0()) sh->released[it].fetch_add(1, std::memory_order_acq_rel); }
     void acc_commit() {}
     void acc_wait() { pthread_barrier_wait(&sh->bar); }
     void tmem_ld16(int lq, int col, float (&v)[16]) {
@@ -142,17 +165,20 @@ void run_tc(const TileArgs& a, int ntiles) {
     sh.tmem.assign(128 * 256, 0.0f);
     sh.tape = a.tape;
     pthread_barrier_init(&sh.bar, nullptr, kThreads);
-    const long total = (long)ntiles * a.T * TapeTC<SR16>::nslab;
-    long pre = 0;
+    const int total = (int)((long)ntiles * a.T * TapeTC<SR16>::nslab);
+    sh.released.reset(new std::atomic<int>[total + 1]);
+    for (int i = 0; i <= total; i++) sh.released[i] = 0;
+    int pre = 0;
     {
         EmuEnvTC<SR16> e0{&sh, 0};
-        for (long i = 0; i < kStages && i < total; i++) { e0.issue(i); pre = i + 1; }
+        for (int i = 0; i < kTcStages && i < total; i++) { e0.issue(i); pre = i + 1; }
+        sh.landed = pre;
     }
     std::vector<std::thread> th;
     for (int t = 0; t < kThreads; t++)
         th.emplace_back([&, t] {
             EmuEnvTC<SR16> env{&sh, t};
-            env.issued = pre;
+            env.issued = pre;   // (only the ring warp uses it)
             run_cta_tc<SR16, RM, S>(env, a, 0, 1, ntiles);
         });
     for (auto& x : th) x.join();

@@ -1,0 +1,32 @@
+"""Per-phase clock64 stamps of one step of the tensor-core kernel (CTA 0): python tools/tc_phase_times.py [B] [T] [rows]"""
+import ctypes, sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from silero_vad_b200 import load_silero_vad, _cabi
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+rows = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+m = load_silero_vad(device=0)
+m.engine.set_kernel("tc"); m.engine.set_tile_rows(rows)
+L = _cabi.lib()
+L.svad_engine_set_debug_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+dbg = torch.zeros(32, dtype=torch.int64, device="cuda")
+L.svad_engine_set_debug_buffer(m.engine._h, dbg.data_ptr())
+x = torch.randn(B, 512 * T, device="cuda") * 0.03
+p = torch.empty(B, T, device="cuda")
+for _ in range(3):
+    m.engine.forward_device(16000, B, 512 * T, 512 * T, x.data_ptr(), 0, 0, 0, 0, p.data_ptr(), T, torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+dbg.zero_()
+m.engine.forward_device(16000, B, 512 * T, 512 * T, x.data_ptr(), 0, 0, 0, 0, p.data_ptr(), T, torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+d = dbg.cpu().tolist()
+names = ["STFT", "lo-stage enc0 + sync", "enc0 MMA issue loop", "enc0 MMA tail (acc_wait)", "enc0 epilogue", "enc1-3 (CUDA cores)", "lo-stage LSTM + sync",
+         "LSTM MMA issue loop", "LSTM MMA tail", "LSTM epilogue + head"]
+tot = d[10] - d[0]
+for i, n in enumerate(names):
+    print(f"{n:28s} {d[i+1]-d[i]:8d} cycles  {100*(d[i+1]-d[i])/tot:5.1f}%")
+print(f"{'step total':28s} {tot:8d} cycles")
+print(f"enc0 loop: slab_wait {d[11]} cycles, free_upto {d[12]} cycles;  LSTM loop: slab_wait {d[13]}, free_upto {d[14]}")
+print(f"LSTM warp0: MMA blocks (16 slabs, 96 MMAs) {d[15]} cycles, commits {d[16]}, skips (48) {d[17]}")
