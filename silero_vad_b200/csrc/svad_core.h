@@ -466,9 +466,10 @@ SVAD_HD void enc0_store(const Tc& tc, float* sm, const Regs& rg) {
 }
 
 // ---------------------------------------------------------------- enc1: 128 -> 64, stride 2, T 4 -> 2
-// One output column o = 8*warp + ln per thread; accumulators are ROW pairs: rg.acc[t*4 + ip] = rows (2ip, 2ip+1).
-// slab = W1p[c][j][64] for channels [c0, c1).  t=0 sees frames (-1,0,1) -> taps 1,2 ; t=1 sees frames (1,2,3).
-// (With RM = 7 the unused 8th row is computed along: its inputs are finite zeros/garbage of an invalid slot.)
+// t=0 sees frames (-1,0,1) -> taps 1,2 ; t=1 sees frames (1,2,3).  Only 64 output columns: a thread owns a column PAIR
+// (oc = 16*(warp&3) + 2*ln, packed FFMA2 with the activation as the scalar operand, like enc0) and the input channels of
+// every slab are split between the two warp groups (warps 0-3 / 4-7); the two partial sums meet in shared memory.
+// rg.acc[t*8 + i] = (col oc, col oc+1) for out-frame t, row i.  slab = W1p[c][j][64] for channels [c0, c1).
 SVAD_HD void load8p(const float* row, int lm, int key, f2 (&x)[4]) {
     f4 a = *reinterpret_cast<const f4*>(row + ((lm ^ key) << 2));
     f4 b = *reinterpret_cast<const f4*>(row + (((4 + lm) ^ key) << 2));
@@ -476,52 +477,76 @@ SVAD_HD void load8p(const float* row, int lm, int key, f2 (&x)[4]) {
 }
 template <int RM, class M = SmemMap>
 SVAD_HD void enc1_init(const Tc& tc, const float* sm, Regs& rg) {
-    const float b = sm[M::consts + M::c_b1 + 8 * tc.warp + tc.ln];
+    const int oc = 16 * (tc.warp & 3) + 2 * tc.ln;
+    const f2 b = (tc.warp < 4) ? *reinterpret_cast<const f2*>(sm + M::consts + M::c_b1 + oc) : f2{0.0f, 0.0f};
 #pragma unroll
-    for (int k = 0; k < 8; k++) rg.acc[k] = f2{b, b};
+    for (int k = 0; k < 16; k++) rg.acc[k] = b;
 }
-SVAD_HD void enc1_fetch(const Tc& tc, const float* e0, const float* wp, int c, f2 (&x)[4][4], float (&w)[3]) {
+SVAD_HD void enc1_fetch(const Tc& tc, const float* e0, const float* wp, int c, float (&x)[4][8], f2 (&w)[3]) {
 #pragma unroll
-    for (int f = 0; f < 4; f++) load8p(e0 + (f * 128 + c) * kSlots, tc.lm, key_hi(c), x[f]);
-    w[0] = wp[0]; w[1] = wp[64]; w[2] = wp[128];
+    for (int f = 0; f < 4; f++) load8(e0 + (f * 128 + c) * kSlots, tc.lm, key_hi(c), x[f]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) w[j] = *reinterpret_cast<const f2*>(wp + j * 64);
 }
-SVAD_HD void enc1_fma(const f2 (&x)[4][4], const float (&w)[3], Regs& rg) {
+template <int RM>
+SVAD_HD void enc1_fma(const float (&x)[4][8], const f2 (&w)[3], Regs& rg) {
 #pragma unroll
-    for (int ip = 0; ip < 4; ip++) {
-        rg.acc[ip] = ffma2_s(w[1], x[0][ip], rg.acc[ip]);
-        rg.acc[ip] = ffma2_s(w[2], x[1][ip], rg.acc[ip]);
-        rg.acc[4 + ip] = ffma2_s(w[0], x[1][ip], rg.acc[4 + ip]);
-        rg.acc[4 + ip] = ffma2_s(w[1], x[2][ip], rg.acc[4 + ip]);
-        rg.acc[4 + ip] = ffma2_s(w[2], x[3][ip], rg.acc[4 + ip]);
+    for (int i = 0; i < RM; i++) {
+        rg.acc[i] = ffma2_s(x[0][i], w[1], rg.acc[i]);
+        rg.acc[i] = ffma2_s(x[1][i], w[2], rg.acc[i]);
+        rg.acc[8 + i] = ffma2_s(x[1][i], w[0], rg.acc[8 + i]);
+        rg.acc[8 + i] = ffma2_s(x[2][i], w[1], rg.acc[8 + i]);
+        rg.acc[8 + i] = ffma2_s(x[3][i], w[2], rg.acc[8 + i]);
     }
 }
 template <int RM, class M = SmemMap>
 SVAD_HD void enc1_slab(const Tc& tc, const float* sm, const float* slab, Regs& rg, int c0, int c1) {
-    const float* wp = slab + 8 * tc.warp + tc.ln;
+    const int hc = (c1 - c0) >> 1, cb = c0 + (tc.warp >> 2) * hc;   // this warp group's channels [cb, cb + hc), hc even
+    const float* wp = slab + (cb - c0) * 192 + 16 * (tc.warp & 3) + 2 * tc.ln;
     const float* e0 = sm + M::e0;
-    f2 xa[4][4], xb[4][4];
-    float wa[3], wb[3];
-    enc1_fetch(tc, e0, wp, c0, xa, wa);
-#pragma unroll 2
-    for (int c = c0; c < c1; c += 2) {   // slabs hold an even number of channels (32)
-        enc1_fetch(tc, e0, wp + (c + 1 - c0) * 192, c + 1, xb, wb);
-        enc1_fma(xa, wa, rg);
-        if (c + 2 < c1) enc1_fetch(tc, e0, wp + (c + 2 - c0) * 192, c + 2, xa, wa);
-        enc1_fma(xb, wb, rg);
+    float xa[4][8], xb[4][8];
+    f2 wa[3], wb[3];
+    enc1_fetch(tc, e0, wp, cb, xa, wa);
+#pragma unroll 1
+    for (int c = 0; c < hc; c += 2) {
+        enc1_fetch(tc, e0, wp + (c + 1) * 192, cb + c + 1, xb, wb);
+        enc1_fma<RM>(xa, wa, rg);
+        if (c + 2 < hc) enc1_fetch(tc, e0, wp + (c + 2) * 192, cb + c + 2, xa, wa);
+        enc1_fma<RM>(xb, wb, rg);
+    }
+}
+// after the last slab: warps 4-7 park their partial sums (scratch above e3), barrier, warps 0-3 add, ReLU, store e1
+template <int RM, class M = SmemMap>
+SVAD_HD void enc1_park(const Tc& tc, float* sm, const Regs& rg) {
+    if (tc.warp < 4) return;
+    float* scr = sm + M::e3 + 128 * kSlots;
+    const int oc = 16 * (tc.warp & 3) + 2 * tc.ln;
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        float v0[8], v1[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { v0[i] = rg.acc[t * 8 + i].x; v1[i] = rg.acc[t * 8 + i].y; }
+        store8(scr + (t * 64 + oc) * kSlots, tc.lm, key_hi(oc), v0);
+        store8(scr + (t * 64 + oc + 1) * kSlots, tc.lm, key_hi(oc), v1);
     }
 }
 template <int RM, class M = SmemMap>
 SVAD_HD void enc1_store(const Tc& tc, float* sm, const Regs& rg) {
-    const int o = 8 * tc.warp + tc.ln;
+    if (tc.warp >= 4) return;
+    const float* scr = sm + M::e3 + 128 * kSlots;
+    const int oc = 16 * tc.warp + 2 * tc.ln;
 #pragma unroll
     for (int t = 0; t < 2; t++) {
-        float v[8];
+        float p0[8], p1[8], v0[8], v1[8];
+        load8(scr + (t * 64 + oc) * kSlots, tc.lm, key_hi(oc), p0);
+        load8(scr + (t * 64 + oc + 1) * kSlots, tc.lm, key_hi(oc), p1);
 #pragma unroll
-        for (int ip = 0; ip < 4; ip++) {
-            v[2 * ip] = (2 * ip < RM) ? relu(rg.acc[t * 4 + ip].x) : 0.0f;
-            v[2 * ip + 1] = (2 * ip + 1 < RM) ? relu(rg.acc[t * 4 + ip].y) : 0.0f;
+        for (int i = 0; i < 8; i++) {
+            v0[i] = (i < RM) ? relu(rg.acc[t * 8 + i].x + p0[i]) : 0.0f;
+            v1[i] = (i < RM) ? relu(rg.acc[t * 8 + i].y + p1[i]) : 0.0f;
         }
-        store8(sm + M::e1 + (t * 64 + o) * kSlots, tc.lm, key_lo(o), v);
+        store8(sm + M::e1 + (t * 64 + oc) * kSlots, tc.lm, key_lo(oc), v0);
+        store8(sm + M::e1 + (t * 64 + oc + 1) * kSlots, tc.lm, key_lo(oc + 1), v1);
     }
 }
 

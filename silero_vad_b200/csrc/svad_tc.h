@@ -293,12 +293,19 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
             enc1_init<RM, M>(tc, sm, rg);
 #pragma unroll 1
             for (int s = 0; s < TP::e1_nslab; s++, it++) {
+                SVAD_CLK(w0);
                 const float* slab = env.slab_wait(it);
+                SVAD_CLK(w1); SVAD_ACC(18, w1 - w0);
                 enc1_slab<RM, M>(tc, sm, slab, rg, s * 16, s * 16 + 16);
-                if (s == TP::e1_nslab - 1) enc1_store<RM, M>(tc, sm, rg);
+                if (s == TP::e1_nslab - 1) enc1_park<RM, M>(tc, sm, rg);
+                SVAD_CLK(w2); SVAD_ACC(19, w2 - w1);
                 env.sync();
+                SVAD_CLK(w3); SVAD_ACC(20, w3 - w2);
                 if (tc.warp == kRingWarp) { env.mark_free(it); env.refill_upto(it + kTcStages, total_slabs); }
             }
+            enc1_store<RM, M>(tc, sm, rg);
+            env.sync();
+            SVAD_STAMP(21);
 #pragma unroll 1
             for (int s = 0; s < 2; s++, it++) {
                 const float* slab = env.slab_wait(it);
@@ -306,6 +313,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 env.sync();
                 if (tc.warp == kRingWarp) { env.mark_free(it); env.refill_upto(it + kTcStages, total_slabs); }
             }
+            SVAD_STAMP(22);
 #pragma unroll 1
             for (int s = 0; s < 2; s++, it++) {
                 const float* slab = env.slab_wait(it);

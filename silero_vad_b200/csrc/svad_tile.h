@@ -147,6 +147,8 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                 enc1_slab<RM>(tc, sm, slab, rg, s * 32, s * 32 + 32);
                 env.slab_done(it);
             }
+            enc1_park<RM>(tc, sm, rg);
+            env.sync();
             enc1_store<RM>(tc, sm, rg);
             env.sync();
             // ---------------- enc2, enc3

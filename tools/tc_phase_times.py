@@ -30,3 +30,4 @@ for i, n in enumerate(names):
 print(f"{'step total':28s} {tot:8d} cycles")
 print(f"enc0 loop: slab_wait {d[11]} cycles, free_upto {d[12]} cycles;  LSTM loop: slab_wait {d[13]}, free_upto {d[14]}")
 print(f"LSTM warp0: MMA blocks (16 slabs, 96 MMAs) {d[15]} cycles, commits {d[16]}, skips (48) {d[17]}")
+print(f"enc1: {d[21]-d[5]} cycles total; tid0 slab_wait {d[18]}, compute {d[19]}, sync {d[20]};  enc2: {d[22]-d[21]};  enc3: {d[6]-d[22]}")
