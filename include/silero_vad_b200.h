@@ -45,8 +45,9 @@ void svad_engine_destroy(svad_engine* e);
 
 /* Streams per CTA tile = 4*rows; rows in [4,8], 0 = choose per call (default). Testing / tuning knob. */
 int svad_engine_set_tile_rows(svad_engine* e, int rows);
-/* Kernel selection: 0 = fp32 CUDA-core kernel (default), 1 = tensor-core kernel (tcgen05, split-precision TF32 for
- * enc0 and the LSTM cell; probabilities agree with the fp32 kernel to ~1e-6). */
+/* Kernel selection: 1 = tensor-core kernel (default: tcgen05, split-precision TF32 for enc0 and the LSTM cell,
+ * everything else fp32 on the CUDA cores), 0 = all-fp32 CUDA-core kernel.  Both meet the parity bar; their
+ * probabilities differ by ~5e-6. */
 int svad_engine_set_kernel(svad_engine* e, int kernel);
 /* Number of SMs of the engine's device. */
 int svad_engine_sm_count(const svad_engine* e);

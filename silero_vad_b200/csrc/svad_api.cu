@@ -302,7 +302,7 @@ struct svad_engine {
     float* d_consts[2] = {nullptr, nullptr};
     float* d_tape_tc[2] = {nullptr, nullptr};  // tensor-core kernel
     float* d_consts_tc[2] = {nullptr, nullptr};
-    int kernel = 0;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32
+    int kernel = 1;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32 (default)
     long long* dbg = nullptr;
     int64_t launches = 0;
     // staging for the host-buffer entry points

@@ -22,10 +22,13 @@ def torch_cuda():
     return torch
 
 
-@pytest.fixture(scope="module")
-def model(torch_cuda):
+@pytest.fixture(scope="module", params=["tc", "fp32"])
+def model(torch_cuda, request):
+    """Both kernels behind the same surface: the tensor-core kernel (default) and the fp32 CUDA-core kernel."""
     from silero_vad_b200 import load_silero_vad
-    return load_silero_vad(device=0)
+    m = load_silero_vad(device=0)
+    m.engine.set_kernel(request.param)
+    return m
 
 
 def seg(ts):
@@ -90,8 +93,9 @@ def test_stateless_step_contract(torch_cuda, model, synthetic, sr):
     torch.cuda.synchronize()
     e_p = float(np.abs(probs.t().cpu().numpy() - s[f"r1_{sr}_probs"]).max())
     e_s = float(np.abs(st.cpu().numpy() - s[f"r1_{sr}_stateN"]).max())
-    print(f"step sr={sr}: prob err {e_p:.3e}, state err {e_s:.3e}")
-    assert e_p < TIGHT and e_s < TIGHT
+    s_tol = TIGHT * max(1.0, float(np.abs(s[f"r1_{sr}_stateN"]).max()))   # the cell state reaches |c| ~ 40 on the loud rows
+    print(f"step sr={sr}: prob err {e_p:.3e}, state err {e_s:.3e} (tol {s_tol:.1e})")
+    assert e_p < TIGHT and e_s < s_tol
     # bulk entry with the same carried-in state/context must agree with the chained steps
     st2 = torch.from_numpy(s[f"r1_{sr}_state0"]).cuda()
     cx2 = torch.from_numpy(s[f"r1_{sr}_ctx0"]).cuda()
@@ -100,7 +104,7 @@ def test_stateless_step_contract(torch_cuda, model, synthetic, sr):
                                 cx2.data_ptr(), pb.data_ptr(), T, stream)
     torch.cuda.synchronize()
     assert float(np.abs(pb.cpu().numpy() - s[f"r1_{sr}_probs"]).max()) < TIGHT
-    assert float(np.abs(st2.cpu().numpy() - s[f"r1_{sr}_stateN"]).max()) < TIGHT
+    assert float(np.abs(st2.cpu().numpy() - s[f"r1_{sr}_stateN"]).max()) < s_tol
     assert np.array_equal(cx2.cpu().numpy(), s[f"r1_{sr}_ctxN"])
 
 
@@ -179,7 +183,7 @@ def test_host_entry_points(torch_cuda, model, synthetic, oracle):
     model.engine.forward_host(sr, B, L, L, x.ctypes.data, st.ctypes.data, cx.ctypes.data, st.ctypes.data, cx.ctypes.data,
                               probs.ctypes.data, T)
     assert float(np.abs(probs - synthetic["r1_16000_probs"]).max()) < TIGHT
-    assert float(np.abs(st - synthetic["r1_16000_stateN"]).max()) < TIGHT
+    assert float(np.abs(st - synthetic["r1_16000_stateN"]).max()) < TIGHT * max(1.0, float(np.abs(synthetic["r1_16000_stateN"]).max()))
     assert np.array_equal(cx, synthetic["r1_16000_ctxN"])
     x1 = np.concatenate([synthetic["r1_16000_ctx0"], x[:, :512]], 1)
     st = synthetic["r1_16000_state0"].copy()

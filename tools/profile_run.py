@@ -9,7 +9,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 sr = int(sys.argv[3]) if len(sys.argv) > 3 else 16000
 rows = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-kernel = sys.argv[5] if len(sys.argv) > 5 else "fp32"
+kernel = sys.argv[5] if len(sys.argv) > 5 else "tc"
 n = 512 if sr == 16000 else 256
 m = load_silero_vad(device=0)
 m.engine.set_tile_rows(rows)
