@@ -112,7 +112,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 }
 // instruction descriptor: D fp32, A/B tf32, A K-major, B MN-major, N = 32, M = 128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = 512;   // enc0 D 0..127, LSTM gates 128..255, enc0 D2 (w_lo terms) 256..383
 
 template <bool SR16>
 struct GpuEnvTC {

@@ -228,19 +228,22 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     SVAD_CLK(c0);
                     const float* tile = env.slab_wait(is);
                     SVAD_CLK(c1); SVAD_ACC(11, c1 - c0);
-                    if (tc.warp == 0) {
+                    // warp 0 issues the w_hi slabs into D (TMEM columns 0..127), warp 1 the w_lo slabs into a second
+                    // accumulator D2 (columns 256..383) so the two issue streams never touch the same accumulator;
+                    // the epilogue adds them.
+                    if (tc.warp == lo) {
                         const int f0 = (j == 2) ? 1 : 0, t0 = f0 + 1 - j, nf = (j == 1) ? 4 : 3;
                         const auto ad = env.mma_a(tile);
                         const auto bh = env.mma_b(sm + M::mag + (f0 * M::mag_pitch + kc * 32) * kSlots, M::mag_pitch * kSlots * 4);
                         const auto bl = env.mma_b(sm + M::lo0 + (f0 * Kt + kc * 32) * kSlots, Kt * kSlots * 4);
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
+                            const bool first = (kc == 0) && (ks == 0) && (jo == 0);
                             if (!lo) {
-                                const bool first = (kc == 0) && (ks == 0) && (jo == 0);
-                                env.mma(t0 * 32, ad, bh, ks, !first, 32 * nf);   // w_hi * x_hi
-                                env.mma(t0 * 32, ad, bl, ks, true, 32 * nf);     // w_hi * x_lo
+                                env.mma(t0 * 32, ad, bh, ks, !first, 32 * nf);         // w_hi * x_hi
+                                env.mma(t0 * 32, ad, bl, ks, true, 32 * nf);           // w_hi * x_lo
                             } else {
-                                env.mma(t0 * 32, ad, bh, ks, true, 32 * nf);     // w_lo * x_hi
+                                env.mma(256 + t0 * 32, ad, bh, ks, !first, 32 * nf);   // w_lo * x_hi
                             }
                         }
                         env.mma_slab_done(is);
@@ -269,12 +272,15 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 for (int ff = 0; ff < 2; ff++) {
                     const int tt = 2 * half + ff;
                     float v[32];
+                    float v2[32];
                     env.tmem_ld16(lq, tt * 32, *reinterpret_cast<float(*)[16]>(v));
                     env.tmem_ld16(lq, tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v + 16));
+                    env.tmem_ld16(lq, 256 + tt * 32, *reinterpret_cast<float(*)[16]>(v2));
+                    env.tmem_ld16(lq, 256 + tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v2 + 16));
                     const float* nyq = sm + M::mag + (M::mag_pitch * tt + Kt) * kSlots;   // row Kt of frame tt (identity swizzle)
 #pragma unroll
                     for (int s = 0; s < 32; s++) {
-                        float acc = v[s] + b0;
+                        float acc = (v[s] + v2[s]) + b0;
                         if (tt > 0) acc = fmaf(wn0, nyq[s - M::mag_pitch * kSlots], acc);
                         acc = fmaf(wn1, nyq[s], acc);
                         if (tt < 3) acc = fmaf(wn2, nyq[s + M::mag_pitch * kSlots], acc);

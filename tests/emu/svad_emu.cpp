@@ -84,7 +84,7 @@ void run(const TileArgs& a, int ntiles) {
 namespace {
 struct SharedTC {
     std::vector<float> smem;
-    std::vector<float> tmem;   // [128 lanes][256 columns]
+    std::vector<float> tmem;   // [128 lanes][512 columns]
     pthread_barrier_t bar;
     const float* tape;
     std::atomic<int> landed{0};                      // slabs copied into the ring so far ("full" barriers)
@@ -143,7 +143,7 @@ struct EmuEnvTC {
                     const float bv = b_rows[kk * 32 + ((((nn >> 3) ^ (kk & 3)) << 3) | (nn & 7))];   // rows start at a multiple of 8: (row & 3) == (kk & 3)
                     s += (double)tf32_trunc(av) * (double)tf32_trunc(bv);
                 }
-                float& d = sh->tmem[r * 256 + col + n];
+                float& d = sh->tmem[r * 512 + col + n];
                 d = (acc ? d : 0.0f) + (float)s;
             }
         }
@@ -154,7 +154,7 @@ struct EmuEnvTC {
     void acc_wait() { pthread_barrier_wait(&sh->bar); }
     void tmem_ld16(int lq, int col, float (&v)[16]) {
         const int lane = 32 * lq + (tid_ & 31);
-        for (int i = 0; i < 16; i++) v[i] = sh->tmem[lane * 256 + col + i];
+        for (int i = 0; i < 16; i++) v[i] = sh->tmem[lane * 512 + col + i];
     }
 };
 
@@ -162,7 +162,7 @@ template <bool SR16, int RM, typename S>
 void run_tc(const TileArgs& a, int ntiles) {
     SharedTC sh;
     sh.smem.assign(SmemMapTC::total_floats, 0.0f);
-    sh.tmem.assign(128 * 256, 0.0f);
+    sh.tmem.assign(128 * 512, 0.0f);
     sh.tape = a.tape;
     pthread_barrier_init(&sh.bar, nullptr, kThreads);
     const int total = (int)((long)ntiles * a.T * TapeTC<SR16>::nslab);

@@ -101,6 +101,7 @@ def emu():
     lib = ctypes.CDLL(str(so))
     fp = ctypes.c_void_p
     lib.svad_emu_forward.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long, fp, ctypes.c_int, fp, fp, fp, fp, fp]
+    lib.svad_emu_forward_tc.argtypes = lib.svad_emu_forward.argtypes
     return lib
 
 
@@ -124,6 +125,29 @@ def test_emulated_kernel_matches_oracle(emu, oracle, fixtures, sr, rm, B):
     assert rc == 0
     assert np.abs(probs - want).max() < 2e-5
     assert np.abs(st_e - st_o).max() < 2e-5
+    assert np.array_equal(cx_e, cx_o)
+
+
+@pytest.mark.parametrize("sr,rm,B", [(16000, 8, 5), (16000, 7, 37), (8000, 8, 5)])
+def test_emulated_tensor_core_kernel_matches_oracle(emu, oracle, fixtures, sr, rm, B):
+    """The tensor-core schedule (svad_tc.h) on CPU threads: tcgen05.mma modelled as truncated-TF32 products read through
+    the declared swizzled layouts, split precision hi/lo, TMEM as an array.  Checks layouts, ring hand-off, epilogues."""
+    from silero_vad_b200.model import WEIGHTS
+    n, ctx = (512, 64) if sr == 16000 else (256, 32)
+    a = fixtures["test16k"]["audio"]
+    dec = 1 if sr == 16000 else 2
+    x = np.stack([a[(9000 * b)::dec][: n * 4 - 37] for b in range(B)]).copy()
+    st = (np.random.default_rng(1).standard_normal((2, B, 128)) * 0.1).astype(np.float32)
+    cx = (np.random.default_rng(2).standard_normal((B, ctx)) * 0.1).astype(np.float32)
+    st_o, cx_o = st.copy(), cx.copy()
+    want = oracle.audio_forward(x, sr, state=st_o, context=cx_o, nthreads=2)
+    probs = np.zeros_like(want)
+    st_e, cx_e = np.zeros_like(st), np.zeros_like(cx)
+    rc = emu.svad_emu_forward_tc(str(WEIGHTS).encode(), sr, rm, B, x.shape[1], x.ctypes.data, 0, st.ctypes.data, cx.ctypes.data,
+                                 st_e.ctypes.data, cx_e.ctypes.data, probs.ctypes.data)
+    assert rc == 0
+    assert np.abs(probs - want).max() < 2e-5
+    assert np.abs(st_e - st_o).max() < 5e-5
     assert np.array_equal(cx_e, cx_o)
 
 
