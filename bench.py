@@ -281,6 +281,30 @@ def run_b200(args):
     }
     if e2e:
         out["e2e"] = e2e
+    if world == 1:
+        # BASELINE configs[1]: batch = 1 streaming, one 512-sample chunk per call through the stateless C ABI step
+        # (host buffers, H2D + cluster kernel + D2H + sync per call)
+        n1 = 512 if sr == 16000 else 256
+        x1 = np.zeros((1, n1 + n1 // 8), np.float32)
+        st1 = np.zeros((2, 1, 128), np.float32)
+        pr1 = np.zeros(1, np.float32)
+        lat = []
+        for i in range(300):
+            x1[0, n1 // 8:] = np.random.default_rng(i).standard_normal(n1).astype(np.float32) * 0.03
+            t0 = time.perf_counter()
+            eng.step_host(sr, 1, x1.ctypes.data, st1.ctypes.data, pr1.ctypes.data, st1.ctypes.data)
+            lat.append((time.perf_counter() - t0) * 1e6)
+        lat = np.sort(np.asarray(lat[50:]))
+        xs = torch.randn(1, n1 * 256, device=dev) * 0.03
+        ps = torch.empty(1, 256, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.forward_device(sr, 1, n1 * 256, n1 * 256, xs.data_ptr(), 0, 0, 0, 0, ps.data_ptr(), 256, stream)
+        e0.record()
+        eng.forward_device(sr, 1, n1 * 256, n1 * 256, xs.data_ptr(), 0, 0, 0, 0, ps.data_ptr(), 256, stream)
+        e1.record(); torch.cuda.synchronize()
+        out["latency_b1"] = {"step_host_us_median": float(np.median(lat)), "step_host_us_p99": float(lat[int(0.99 * len(lat))]),
+                             "kernel_us_per_chunk": e0.elapsed_time(e1) * 1e3 / 256,
+                             "note": "batch=1 (BASELINE configs[1]): svad_step_host per chunk incl. copies and sync; kernel = 8-CTA cluster kernel, 256 chunks in one launch"}
     if world == 1 and not args.no_cpu_baseline:
         o, xs, Ts, Bs, threads = cpu_arm(args)
         t0 = time.perf_counter(); o.audio_forward(xs, sr, nthreads=threads); dt = time.perf_counter() - t0

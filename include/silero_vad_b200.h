@@ -49,6 +49,9 @@ int svad_engine_set_tile_rows(svad_engine* e, int rows);
  * everything else fp32 on the CUDA cores), 0 = all-fp32 CUDA-core kernel.  Both meet the parity bar; their
  * probabilities differ by ~5e-6. */
 int svad_engine_set_kernel(svad_engine* e, int kernel);
+/* Batches of up to `streams` streams run on the small-batch cluster kernel (8-CTA clusters with the network split
+ * across their shared memories; the latency path).  Default 256 (measured crossover with the tile kernels); 0 disables it. */
+int svad_engine_set_small_batch_max(svad_engine* e, int streams);
 /* Number of SMs of the engine's device. */
 int svad_engine_sm_count(const svad_engine* e);
 /* Kernel launches issued by this engine so far (bench.py's gpu_launches). */

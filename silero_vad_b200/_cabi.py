@@ -11,7 +11,7 @@ _f32p = ctypes.c_void_p  # device or host float* passed as an integer address
 _lib = None
 
 EXPORTS = ["svad_abi_version", "svad_last_error", "svad_engine_create", "svad_engine_destroy",
-           "svad_engine_set_tile_rows", "svad_engine_set_kernel", "svad_engine_sm_count", "svad_engine_launch_count",
+           "svad_engine_set_tile_rows", "svad_engine_set_kernel", "svad_engine_set_small_batch_max", "svad_engine_sm_count", "svad_engine_launch_count",
            "svad_forward_device", "svad_forward_device_pcm16", "svad_step_device", "svad_forward_host",
            "svad_forward_host_pcm16", "svad_step_host",
            "svad_segment_params_default", "svad_speech_segments"]
@@ -46,6 +46,7 @@ def lib():
     L.svad_engine_destroy.restype = None
     L.svad_engine_set_tile_rows.argtypes = [vp, i32]
     L.svad_engine_set_kernel.argtypes = [vp, i32]
+    L.svad_engine_set_small_batch_max.argtypes = [vp, i32]
     L.svad_engine_sm_count.argtypes = [vp]
     L.svad_engine_launch_count.argtypes = [vp]
     L.svad_engine_launch_count.restype = i64
@@ -98,6 +99,9 @@ class Engine:
     def set_kernel(self, kernel):
         """0 / 'fp32' = CUDA-core kernel, 1 / 'tc' = tcgen05 split-TF32 kernel."""
         check(lib().svad_engine_set_kernel(self._h, {"fp32": 0, "tc": 1}.get(kernel, kernel)))
+
+    def set_small_batch_max(self, streams):
+        check(lib().svad_engine_set_small_batch_max(self._h, streams))
 
     def set_tile_rows(self, rows):
         check(lib().svad_engine_set_tile_rows(self._h, rows))

@@ -8,6 +8,7 @@
 // two-stage shared-memory ring with cp.async.bulk (TMA bulk copy, completion on an mbarrier) one slab
 // ahead of the FFMA loops.  HBM traffic is the audio read once plus 4 B per chunk of probabilities.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -17,6 +18,7 @@
 
 #include "../../include/silero_vad_b200.h"
 #include "svad_tc.h"
+#include "svad_small.h"
 
 using namespace svad;
 
@@ -277,6 +279,243 @@ __global__ void __launch_bounds__(kThreads, 1) svad_fused_tc(TileArgs a, int nti
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(env.tmem), "r"(kTmemCols) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------ small-batch cluster kernel
+namespace cg = cooperative_groups;
+
+template <bool SR16, typename S>
+__global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs a, const float* __restrict__ blobs) {
+    using G = Geo<SR16>;
+    using M = SmallMap<SR16>;
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    const int cid = (int)blockIdx.x / kSmallCtas;
+    const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g0 = cid * kSmallNS;
+    const S* audio = static_cast<const S*>(a.audio);
+
+    {   // this CTA's slice of every layer -> shared memory, resident for the whole launch
+        const float4* src = reinterpret_cast<const float4*>(blobs + (size_t)r * M::blob_floats);
+        float4* dst = reinterpret_cast<float4*>(sm);
+        for (int i = tid; i < M::blob_floats / 4; i += kSmallThreads) dst[i] = __ldg(src + i);
+    }
+    float* peer[kSmallCtas];
+#pragma unroll
+    for (int q = 0; q < kSmallCtas; q++) peer[q] = cluster.map_shared_rank(sm, q);
+    // h lives twice (ping-pong by step parity) so the gather of h' never races the peers still reading h
+    float* hbuf[2] = {sm + M::a_xh + 128 * 4, sm + M::a_h2};
+    for (int i = tid; i < 128 * 4; i += kSmallThreads) {
+        const int j = i >> 2, st = i & 3, g = g0 + st;
+        hbuf[0][i] = (a.state_in && g < a.B) ? a.state_in[(long)g * kHid + j] : 0.0f;
+    }
+    if (tid < 64) {
+        const int u = tid >> 2, st = tid & 3, g = g0 + st;
+        sm[M::a_c + tid] = (a.state_in && g < a.B) ? a.state_in[((long)a.B + g) * kHid + 16 * r + u] : 0.0f;
+    }
+    __syncthreads();
+    cluster.sync();
+
+    const float4* xp4 = reinterpret_cast<const float4*>(sm + M::a_xp);
+    const float4* mag4 = reinterpret_cast<const float4*>(sm + M::a_mag);
+    const float4* e04 = reinterpret_cast<const float4*>(sm + M::a_e0);
+    const float4* e14 = reinterpret_cast<const float4*>(sm + M::a_e1);
+    const float4* e24 = reinterpret_cast<const float4*>(sm + M::a_e2);
+    const float4* e34 = reinterpret_cast<const float4*>(sm + M::a_xh);
+    float4* red = reinterpret_cast<float4*>(sm + M::a_red);
+    // all-gather one float4 (4 streams of one channel) into the same offset of all 8 CTAs
+    auto gather = [&](int off_floats, float4 v) {
+#pragma unroll
+        for (int q = 0; q < kSmallCtas; q++) *reinterpret_cast<float4*>(peer[q] + off_floats) = v;
+    };
+    auto relu4b = [](float4 v, float b) { return make_float4(fmaxf(v.x + b, 0.f), fmaxf(v.y + b, 0.f), fmaxf(v.z + b, 0.f), fmaxf(v.w + b, 0.f)); };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#define SM_STAMP(k) do { if (a.dbg && blockIdx.x == 0 && t == 2 && tid == 0) a.dbg[k] = clock64(); } while (0)
+    for (long t = 0; t < a.T; t++) {
+        const int cur = (int)(t & 1);
+        SM_STAMP(0);
+        // 1. padded window [context | chunk | reflect] of the 4 streams
+        for (int i = tid; i < (G::L1 + G::N / 4) * 4; i += kSmallThreads) {
+            const int k = i >> 2, st = i & 3, g = g0 + st;
+            float v = 0.0f;
+            if (g < a.B) v = window_sample<SR16, S>(audio + (long)g * a.ld, a.L, a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr, t, k);
+            sm[M::a_xp + i] = v;
+        }
+        __syncthreads();
+        SM_STAMP(1);
+        // 2. STFT slice: thread = (basis row, frame), full K = N
+        if (tid < M::RB * 4) {
+            const int row = tid % M::RB, f = tid / M::RB;
+            float4 acc = zero4;
+            dotT(sm + M::w_basis, M::RB, row, xp4 + f * G::hop, 0, G::N, acc);
+            red[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < M::BPC * 4) {
+            const int lb = tid % M::BPC, f = tid / M::BPC, bin = r * M::BPC + lb;
+            if (bin < G::F) {
+                const float4 re = red[f * M::RB + 2 * lb], im = red[f * M::RB + 2 * lb + 1];
+                gather(M::a_mag + (f * G::F + bin) * 4, make_float4(sqrtf(re.x * re.x + im.x * im.x), sqrtf(re.y * re.y + im.y * im.y),
+                                                                    sqrtf(re.z * re.z + im.z * im.z), sqrtf(re.w * re.w + im.w * im.w)));
+            }
+        }
+        SM_STAMP(2);
+        cluster.sync();
+        SM_STAMP(3);
+        // 3. enc0 slice: thread = (channel o, out frame tt, k-part kp of 4); live taps only
+        {
+            const int o = tid & 15, tt = (tid >> 4) & 3, kp = tid >> 6;
+            constexpr int Cc = (G::F + 3) / 4;
+            const int c0 = kp * Cc, c1 = (c0 + Cc < G::F) ? c0 + Cc : G::F;
+            float4 acc = zero4;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int f = tt + j - 1;
+                if (f < 0 || f > 3) continue;
+                dotT(sm + M::w_e0 + j * G::F * 16, 16, o, mag4 + f * G::F, c0, c1, acc);
+            }
+            red[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < 64) {
+            const int o = tid & 15, tt = tid >> 4;
+            const float4 v = add4(add4(red[tid], red[tid + 64]), add4(red[tid + 128], red[tid + 192]));
+            gather(M::a_e0 + (tt * 128 + 16 * r + o) * 4, relu4b(v, sm[M::w_b0 + o]));
+        }
+        SM_STAMP(4);
+        cluster.sync();
+        SM_STAMP(5);
+        // 4. enc1 slice (stride 2): thread = (o 8, tt 2, kp 16): out frame tt reads frames 2 tt + j - 1, 8 channels per part
+        {
+            const int o = tid & 7, tt = (tid >> 3) & 1, kp = tid >> 4;
+            float4 acc = zero4;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int f = 2 * tt + j - 1;
+                if (f < 0) continue;
+                dotT(sm + M::w_e1 + j * 128 * 8, 8, o, e04 + f * 128, kp * 8, kp * 8 + 8, acc);
+            }
+            red[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < 16) {
+            float4 v = zero4;
+#pragma unroll
+            for (int kp = 0; kp < 16; kp++) v = add4(v, red[tid + 16 * kp]);
+            gather(M::a_e1 + ((tid >> 3) * 64 + 8 * r + (tid & 7)) * 4, relu4b(v, sm[M::w_b1 + (tid & 7)]));
+        }
+        cluster.sync();
+        // 5. enc2 slice (taps 1, 2 live): thread = (o 8, kp 32): K = 2 x 64 in parts of 4
+        {
+            const int o = tid & 7, kp = tid >> 3;
+            float4 acc = zero4;
+            dotT(sm + M::w_e2, 8, o, e14, kp * 4, kp * 4 + 4, acc);   // rows k = jj*64 + c line up with e1[jj][c]
+            red[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < 8) {
+            float4 v = zero4;
+#pragma unroll
+            for (int kp = 0; kp < 32; kp++) v = add4(v, red[tid + 8 * kp]);
+            gather(M::a_e2 + (8 * r + tid) * 4, relu4b(v, sm[M::w_b2 + tid]));
+        }
+        cluster.sync();
+        // 6. enc3 slice (tap 1 live) -> first half of the LSTM input: thread = (o 16, kp 16)
+        {
+            const int o = tid & 15, kp = tid >> 4;
+            float4 acc = zero4;
+            dotT(sm + M::w_e3, 16, o, e24, kp * 4, kp * 4 + 4, acc);
+            red[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < 16) {
+            float4 v = zero4;
+#pragma unroll
+            for (int kp = 0; kp < 16; kp++) v = add4(v, red[tid + 16 * kp]);
+            gather(M::a_xh + (16 * r + tid) * 4, relu4b(v, sm[M::w_b3 + tid]));
+        }
+        cluster.sync();
+        SM_STAMP(6);
+        // 7. LSTM: this CTA's 16 hidden units x 4 gates: thread = (row 64, kp 4), K = [e3 ; h]
+        {
+            const int row = tid & 63, kp = tid >> 6;
+            float4 acc = zero4;
+            if (kp < 2) dotT(sm + M::w_l, 64, row, e34, kp * 64, kp * 64 + 64, acc);
+            else dotT(sm + M::w_l + 128 * 64, 64, row, reinterpret_cast<const float4*>(hbuf[cur]), (kp - 2) * 64, (kp - 2) * 64 + 64, acc);
+            red[tid] = acc;
+        }
+        __syncthreads();
+        if (tid < 64) {
+            const float b = sm[M::w_bl + tid];
+            const float4 v = add4(add4(red[tid], red[tid + 64]), add4(red[tid + 128], red[tid + 192]));
+            *reinterpret_cast<float4*>(sm + M::a_gates + tid * 4) = make_float4(v.x + b, v.y + b, v.z + b, v.w + b);
+        }
+        __syncthreads();
+        if (tid < 64) {
+            const int u = tid >> 2, st = tid & 3;
+            const float* gt = sm + M::a_gates + (u * 4) * 4 + st;
+            const float ig = sigmoid_acc(gt[0]), fg = sigmoid_acc(gt[4]), gg = tanhf(gt[8]), og = sigmoid_acc(gt[12]);
+            const float cn = fmaf(fg, sm[M::a_c + tid], ig * gg);
+            sm[M::a_c + tid] = cn;
+            const float hn = og * tanhf(cn);
+            const int off = (int)(hbuf[cur ^ 1] - sm) + (16 * r + u) * 4 + st;
+#pragma unroll
+            for (int q = 0; q < kSmallCtas; q++) peer[q][off] = hn;
+        }
+        SM_STAMP(7);
+        cluster.sync();
+        SM_STAMP(8);
+        // 8. head (rank 0): 128 threads = (hidden unit j), then a 4-stream reduction through shared memory
+        if (r == 0) {
+            if (tid < 128) {
+                const float4 hv = reinterpret_cast<const float4*>(hbuf[cur ^ 1])[tid];
+                const float wv = sm[M::w_out + tid];
+                red[tid] = make_float4(wv * fmaxf(hv.x, 0.f), wv * fmaxf(hv.y, 0.f), wv * fmaxf(hv.z, 0.f), wv * fmaxf(hv.w, 0.f));
+            }
+            __syncthreads();
+            if (tid < 32) {
+                float4 v = add4(add4(red[tid], red[tid + 32]), add4(red[tid + 64], red[tid + 96]));
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                    v.x += __shfl_xor_sync(0xffffffffu, v.x, o2); v.y += __shfl_xor_sync(0xffffffffu, v.y, o2);
+                    v.z += __shfl_xor_sync(0xffffffffu, v.z, o2); v.w += __shfl_xor_sync(0xffffffffu, v.w, o2);
+                }
+                const float b = sm[M::w_out + 128];
+                if (tid < kSmallNS && g0 + tid < a.B) {
+                    const float x = tid == 0 ? v.x : (tid == 1 ? v.y : (tid == 2 ? v.z : v.w));
+                    a.probs[(long)(g0 + tid) * a.ldp + t] = sigmoid_acc(x + b);
+                }
+            }
+        }
+        SM_STAMP(9);
+    }
+#undef SM_STAMP
+    // carry state / context out
+    const int fin = (int)(a.T & 1);
+    if (a.state_out) {
+        if (r == 0)
+            for (int i = tid; i < 128 * 4; i += kSmallThreads) {
+                const int j = i >> 2, st = i & 3, g = g0 + st;
+                if (g < a.B) a.state_out[(long)g * kHid + j] = hbuf[fin][i];
+            }
+        if (tid < 64) {
+            const int u = tid >> 2, st = tid & 3, g = g0 + st;
+            if (g < a.B) a.state_out[((long)a.B + g) * kHid + 16 * r + u] = sm[M::a_c + tid];
+        }
+    }
+    if (a.ctx_out && r == 0) {
+        for (int i = tid; i < kSmallNS * G::ctx; i += kSmallThreads) {
+            const int st = i / G::ctx, k = i % G::ctx, g = g0 + st;
+            if (g < a.B) {
+                const float* cx = a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr;
+                a.ctx_out[(long)g * G::ctx + k] = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k) : (cx ? cx[k] : 0.0f);
+            }
+        }
+    }
+    cluster.sync();   // nobody exits while a peer may still address its shared memory
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host
@@ -302,6 +541,8 @@ struct svad_engine {
     float* d_consts[2] = {nullptr, nullptr};
     float* d_tape_tc[2] = {nullptr, nullptr};  // tensor-core kernel
     float* d_consts_tc[2] = {nullptr, nullptr};
+    float* d_small[2] = {nullptr, nullptr};    // small-batch cluster kernel: 8 per-CTA weight slices
+    int small_max = 256;                       // streams up to which the cluster kernel is used (0 = never); crossover with the tile kernels measured at ~256
     int kernel = 1;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32 (default)
     long long* dbg = nullptr;
     int64_t launches = 0;
@@ -347,6 +588,10 @@ extern "C" int svad_engine_create(const char* weights_path, int device, svad_eng
         CUDA_TRY(cudaMalloc(&e->d_consts_tc[b], pbt[b].consts.size() * 4));
         CUDA_TRY(cudaMemcpy(e->d_tape_tc[b], pbt[b].tape.data(), pbt[b].tape.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_consts_tc[b], pbt[b].consts.data(), pbt[b].consts.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<float> blobs;
+        if (b == 0) pack_small<true>(tm, blobs); else pack_small<false>(tm, blobs);
+        CUDA_TRY(cudaMalloc(&e->d_small[b], blobs.size() * 4));
+        CUDA_TRY(cudaMemcpy(e->d_small[b], blobs.data(), blobs.size() * 4, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_copy, cudaStreamNonBlocking));
@@ -358,7 +603,7 @@ extern "C" int svad_engine_create(const char* weights_path, int device, svad_eng
 extern "C" void svad_engine_destroy(svad_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    for (int b = 0; b < 2; b++) { cudaFree(e->d_tape[b]); cudaFree(e->d_consts[b]); cudaFree(e->d_tape_tc[b]); cudaFree(e->d_consts_tc[b]); }
+    for (int b = 0; b < 2; b++) { cudaFree(e->d_tape[b]); cudaFree(e->d_consts[b]); cudaFree(e->d_tape_tc[b]); cudaFree(e->d_consts_tc[b]); cudaFree(e->d_small[b]); }
     if (e->h_pin) cudaFreeHost(e->h_pin);
     if (e->d_buf) cudaFree(e->d_buf);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -381,6 +626,11 @@ extern "C" int svad_engine_set_kernel(svad_engine* e, int kernel) {
 extern "C" int svad_engine_set_debug_buffer(svad_engine* e, long long* d_buf) {
     if (!e) return SVAD_EINVAL;
     e->dbg = d_buf;
+    return SVAD_OK;
+}
+extern "C" int svad_engine_set_small_batch_max(svad_engine* e, int streams) {
+    if (!e || streams < 0) return fail(SVAD_EINVAL, "small-batch limit must be >= 0");
+    e->small_max = streams;
     return SVAD_OK;
 }
 extern "C" int svad_engine_sm_count(const svad_engine* e) { return e ? e->sms : 0; }
@@ -418,6 +668,29 @@ static int launch_tc(svad_engine* e, const TileArgs& a, cudaStream_t st) {
     return SVAD_OK;
 }
 
+template <bool SR16, typename S>
+static int launch_small(svad_engine* e, const TileArgs& a, cudaStream_t st) {
+    auto kern = svad_small_cluster<SR16, S>;
+    const size_t smem = (size_t)SmallMap<SR16>::total_floats * 4;
+    static bool configured[16] = {};
+    if (!configured[e->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[e->device & 15] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((a.B + kSmallNS - 1) / kSmallNS * kSmallCtas));
+    cfg.blockDim = dim3(kSmallThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kSmallCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, (const float*)e->d_small[SR16 ? 0 : 1]));
+    e->launches++;
+    return SVAD_OK;
+}
+
 // rows per thread that minimises (waves x rows): the FFMA work of a CTA step is proportional to RM.
 static int pick_rows(const svad_engine* e, int B) {
     if (e->tile_rows) return e->tile_rows;
@@ -434,6 +707,7 @@ static int pick_rows(const svad_engine* e, int B) {
 
 template <bool SR16, typename S>
 static int launch_rm(svad_engine* e, const TileArgs& a, cudaStream_t st) {
+    if (a.B <= e->small_max) return launch_small<SR16, S>(e, a, st);
     if (e->kernel == 1) {   // tensor-core kernel: MMA cost does not depend on the tile rows; only 7 and 8 are built
         if (a.T > 4000000) return fail(SVAD_EINVAL, "tensor-core kernel: at most 4e6 chunks per call (feed long streams in pieces)");
         const int rm = e->tile_rows ? e->tile_rows : pick_rows(e, a.B);

@@ -19,6 +19,7 @@ def model_tc(torch_cuda):
     from silero_vad_b200 import load_silero_vad
     m = load_silero_vad(device=0)
     m.engine.set_kernel("tc")
+    m.engine.set_small_batch_max(0)
     return m
 
 
@@ -89,6 +90,7 @@ def test_tc_matches_fp32_kernel_full_batch(torch_cuda, model_tc, fixtures):
     torch = torch_cuda
     from silero_vad_b200 import load_silero_vad
     ref = load_silero_vad(device=0)
+    ref.engine.set_kernel("fp32")
     a = torch.from_numpy(fixtures["aepyx16k"]["audio"][: 512 * 100 * 8]).view(8, -1)
     x = a.repeat(512, 1).cuda()                      # 4096 streams x 100 chunks
     p_tc = model_tc.audio_forward_device(x, 16000)

@@ -13,7 +13,11 @@ kernel = sys.argv[5] if len(sys.argv) > 5 else "tc"
 n = 512 if sr == 16000 else 256
 m = load_silero_vad(device=0)
 m.engine.set_tile_rows(rows)
-m.engine.set_kernel(kernel)
+if kernel == "small":
+    m.engine.set_small_batch_max(1 << 30)
+else:
+    m.engine.set_kernel(kernel)
+    m.engine.set_small_batch_max(0)
 x = torch.randn(B, n * T, device="cuda") * 0.03
 p = torch.empty(B, T, device="cuda")
 for _ in range(3):
