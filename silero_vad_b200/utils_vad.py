@@ -193,6 +193,70 @@ class VADIterator:
         return None
 
 
+class VADIteratorBatch:
+    """B live streams multiplexed through one model call per chunk period (the telephony case: README.md:132 of the
+    reference).  Each row behaves exactly like its own `VADIterator` (utils_vad.py:458-549):
+    `__call__(x[B, n])` returns a list of B entries, each None / {'start': ..} / {'end': ..}.  Rows can be parked and
+    resumed with `model.get_states()` / `model.set_states()`; `reset_rows(mask)` restarts individual streams."""
+
+    def __init__(self, model, batch_size: int, threshold: float = 0.5, sampling_rate: int = 16000,
+                 min_silence_duration_ms: int = 100, speech_pad_ms: int = 30):
+        if sampling_rate not in [8000, 16000]:
+            raise ValueError('VADIterator does not support sampling rates other than [8000, 16000]')
+        self.model, self.B = model, batch_size
+        self.threshold, self.sampling_rate = threshold, sampling_rate
+        self.min_silence_samples = sampling_rate * min_silence_duration_ms / 1000
+        self.speech_pad_samples = sampling_rate * speech_pad_ms / 1000
+        self.reset_states()
+
+    def reset_states(self):
+        self.model.reset_states()
+        self.triggered = np.zeros(self.B, bool)
+        self.temp_end = np.zeros(self.B, np.int64)
+        self.current_sample = np.zeros(self.B, np.int64)
+
+    def reset_rows(self, mask):
+        """Restart the streams selected by the boolean mask (new call on that line): their LSTM state and audio context
+        are zeroed on the device, their event automaton is cleared; the other rows are untouched."""
+        mask = np.asarray(mask, bool)
+        self.triggered[mask] = False
+        self.temp_end[mask] = 0
+        self.current_sample[mask] = 0
+        st = getattr(self.model, "_state", None)
+        if st is not None and mask.any():
+            m = torch.as_tensor(mask, device=st.device)
+            st[:, m, :] = 0
+            self.model._context[m, :] = 0
+
+    @torch.no_grad()
+    def __call__(self, x, return_seconds=False, time_resolution: int = 1):
+        x = torch.as_tensor(x)
+        if x.dim() != 2 or x.shape[0] != self.B:
+            raise ValueError(f"expected [{self.B}, n] audio chunks")
+        window = x.shape[1]
+        self.current_sample += window
+        prob = self.model(x, self.sampling_rate).reshape(-1).cpu().numpy().astype(np.float64)
+        rising = prob >= self.threshold
+        self.temp_end[rising & (self.temp_end != 0)] = 0
+        out = [None] * self.B
+        start_rows = rising & ~self.triggered
+        for b in np.nonzero(start_rows)[0]:
+            self.triggered[b] = True
+            start = max(0, self.current_sample[b] - self.speech_pad_samples - window)
+            out[b] = {'start': int(start) if not return_seconds else round(start / self.sampling_rate, time_resolution)}
+        falling = (prob < self.threshold - 0.15) & self.triggered & ~start_rows
+        for b in np.nonzero(falling)[0]:
+            if not self.temp_end[b]:
+                self.temp_end[b] = self.current_sample[b]
+            if self.current_sample[b] - self.temp_end[b] < self.min_silence_samples:
+                continue
+            end = self.temp_end[b] + self.speech_pad_samples - window
+            self.temp_end[b] = 0
+            self.triggered[b] = False
+            out[b] = {'end': int(end) if not return_seconds else round(end / self.sampling_rate, time_resolution)}
+        return out
+
+
 def collect_chunks(tss: List[dict], wav: torch.Tensor, seconds: bool = False, sampling_rate: int = None) -> torch.Tensor:
     """Concatenate the audio inside the given segments (utils_vad.py:552-597)."""
     if seconds and not sampling_rate:

@@ -231,3 +231,25 @@ def test_pcm16_paths_bit_identical(torch_cuda, model, fixtures):
             fn(16000, B, L, L, a.data_ptr(), 0, 0, st.ctypes.data, 0, out.data_ptr(), T)
             assert torch.equal(out.cpu(), want), (arr.dtype, pinned)
             assert np.abs(st).max() > 0
+
+
+def test_vad_iterator_batch_on_device(torch_cuda, model, fixtures, meta):
+    """8 phone lines in parallel, each fed a different offset of the fixture: every row must emit what a private
+    VADIterator emits; row 0 (offset 0) must reproduce the reference's golden event list."""
+    torch = torch_cuda
+    from silero_vad_b200 import VADIterator, VADIteratorBatch
+    wav = torch.from_numpy(fixtures["test16k"]["audio"])
+    B, T = 8, 500
+    offs = [0] + [7000 * b + 123 for b in range(1, B)]
+    it = VADIteratorBatch(model, B)
+    got = [[] for _ in range(B)]
+    for t in range(T):
+        x = torch.stack([wav[o + 512 * t: o + 512 * (t + 1)] for o in offs])
+        for b, e in enumerate(it(x)):
+            if e:
+                got[b].append(e)
+    assert got[0] == meta["test16k"]["vad_iterator_events"][:len(got[0])] and len(got[0]) > 6
+    for b in (3, 7):
+        single = VADIterator(model)
+        want = [e for e in (single(wav[offs[b] + 512 * t: offs[b] + 512 * (t + 1)]) for t in range(T)) if e]
+        assert got[b] == want

@@ -178,3 +178,45 @@ def test_validate_input_messages():
         m._validate_input(torch.zeros(512), 22050)
     with pytest.raises(ValueError, match="too short"):
         m._validate_input(torch.zeros(100), 16000)
+
+
+def test_header_is_valid_c():
+    """include/silero_vad_b200.h must compile as plain C (it is what cgo / JNI / Rust bindgen consume)."""
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", str(REPO / "include" / "silero_vad_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+class _ScriptedModel:
+    """Duck-typed model that replays scripted probabilities [T][B] (host logic tests need no GPU)."""
+
+    def __init__(self, probs):
+        import torch
+        self.p, self.i, self.torch = probs, 0, torch
+
+    def reset_states(self):
+        self.i = 0
+
+    def __call__(self, x, sr):
+        row = self.p[self.i]
+        self.i += 1
+        return self.torch.tensor(row, dtype=self.torch.float32).reshape(-1, 1)
+
+
+def test_vad_iterator_batch_equals_independent_iterators():
+    import torch
+    from oracle import oracle as O
+    from silero_vad_b200 import VADIterator, VADIteratorBatch
+    rng = np.random.default_rng(5)
+    B, T = 7, 400
+    probs = np.clip(np.cumsum(rng.normal(0, 0.2, (T, B)), axis=0) % 2.0, 0, 1).astype(np.float32)
+    it = VADIteratorBatch(_ScriptedModel(probs), B)
+    got = [[] for _ in range(B)]
+    for t in range(T):
+        for b, e in enumerate(it(torch.zeros(B, 512))):
+            got[b].append(e)
+    for b in range(B):
+        single = VADIterator(_ScriptedModel(probs[:, b:b + 1]))
+        want = [single(torch.zeros(512)) for _ in range(T)]
+        assert got[b] == want
+        assert want == O.vad_iterator_events(probs[:, b].tolist(), 512)
