@@ -127,8 +127,8 @@ struct GpuEnvTC {
     uint32_t tmem;
     // warp-0 bookkeeping (identical in all its lanes): next slab to issue / last slab known consumed, their position in
     // the per-step schedule, parity bits of the mdone barriers, parity of the accumulator barrier
-    int issued, issued_idx, freed, freed_idx;
-    uint32_t mpar, acc_phase;
+    int issued, issued_idx, freed;
+    uint32_t mpar, fpar, acc_phase;   // parity bits: consumed barriers (ring warp), landed barriers (every consumer), accumulators
     __device__ __forceinline__ int tid() const { return tid_; }
     __device__ __forceinline__ float* smem() { return sm; }
     __device__ __forceinline__ void sync() { __syncthreads(); }
@@ -154,42 +154,42 @@ struct GpuEnvTC {
             "r"(parity)
             : "memory");
     }
-    __device__ __forceinline__ void issue(int it, int idx) {   // one lane
-        const int stage = it & (kTcStages - 1);
-        const uint32_t bytes = (uint32_t)TapeTC<SR16>::slab_len(idx) * 4u;
-        const uint32_t bar = smem_u32(full + stage);
-        const uint32_t dst = smem_u32(sm + SmemMapTC::stage + stage * SmemMapTC::stage_floats);
-        const float* src = tape + TapeTC<SR16>::slab_off(idx);
+    __device__ __forceinline__ void issue(int idx) {   // one lane
+        using TP = TapeTC<SR16>;
+        const int b = TP::buf(idx);
+        const uint32_t bytes = (uint32_t)TP::slab_len(idx) * 4u;
+        const uint32_t bar = smem_u32(full + b);
+        const uint32_t dst = smem_u32(sm + TP::template buf_off<SmemMapTC>(b));
+        const float* src = tape + TP::slab_off(idx);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                      "l"(src), "r"(bytes), "r"(bar)
                      : "memory");
     }
-    __device__ __forceinline__ const float* slab_wait(int it) {
-        const int stage = it & (kTcStages - 1);
-        mbar_wait(smem_u32(full + stage), (uint32_t)((it >> 2) & 1));
-        return sm + SmemMapTC::stage + stage * SmemMapTC::stage_floats;
+    // consumers: wait for the slab with per-step index idx; one parity bit per buffer, flipped at every visit
+    __device__ __forceinline__ const float* slab_wait(int idx) {
+        using TP = TapeTC<SR16>;
+        const int b = TP::buf(idx);
+        mbar_wait(smem_u32(full + b), (fpar >> b) & 1u);
+        fpar ^= 1u << b;
+        return sm + TP::template buf_off<SmemMapTC>(b);
     }
-    __device__ __forceinline__ void advance_freed() {
+    __device__ __forceinline__ void skip_phase(uint32_t mask, int) { fpar ^= mask; }
+    __device__ __forceinline__ void slab_pass(int idx) { fpar ^= 1u << TapeTC<SR16>::buf(idx); }
+    // ring warp
+    __device__ __forceinline__ void wait_consumed_group(int idx, int n) {   // slabs are released in order
+        for (int i = 0; i < n - 1; i++) mpar ^= 1u << TapeTC<SR16>::buf(idx + i);   // their phases complete before the last one's
+        const int b = TapeTC<SR16>::buf(idx + n - 1);
+        mbar_wait(smem_u32(mdone + b), (mpar >> b) & 1u);
+        mpar ^= 1u << b;
+    }
+    __device__ __forceinline__ void ring_freed(int total) {
+        using TP = TapeTC<SR16>;
         freed++;
-        if (++freed_idx == TapeTC<SR16>::nslab) freed_idx = 0;
-    }
-    __device__ __forceinline__ void mark_free(int x) { advance_freed(); (void)x; }   // in order: x == freed + 1
-    __device__ __forceinline__ void free_upto(int x) {
-        while (freed < x) {
-            advance_freed();
-            if (TapeTC<SR16>::is_mma(freed_idx)) {
-                const int st = freed & (kTcStages - 1);
-                mbar_wait(smem_u32(mdone + st), (mpar >> st) & 1u);
-                mpar ^= 1u << st;
-            }
-        }
-    }
-    __device__ __forceinline__ void refill_upto(int x, int total) {
-        while (issued <= x && issued < total) {
-            if (elect()) issue(issued, issued_idx);
+        while (issued < total && issued - TP::dep_delta(issued_idx) <= freed) {
+            if (elect()) issue(issued_idx);
             issued++;
-            if (++issued_idx == TapeTC<SR16>::nslab) issued_idx = 0;
+            if (++issued_idx == TP::nslab) issued_idx = 0;
         }
     }
     // descriptors: low word carries the address; a k-step advances A by 32 B and B by 8 rows = 1024 B
@@ -212,10 +212,10 @@ struct GpuEnvTC {
     }
     __device__ __forceinline__ void mma_slab_done(int it) {
         if (elect())
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mdone + (it & (kTcStages - 1)))) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mdone + TapeTC<SR16>::buf(it))) : "memory");
     }
     __device__ __forceinline__ void slab_skip(int it) {   // an MMA warp that does not read this slab still releases it
-        if (elect()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mdone + (it & (kTcStages - 1)))) : "memory");
+        if (elect()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mdone + TapeTC<SR16>::buf(it))) : "memory");
     }
     __device__ __forceinline__ void acc_commit() {
         if (elect())
@@ -240,30 +240,31 @@ struct GpuEnvTC {
     }
 };
 
-constexpr size_t kSmemBytesTC = (size_t)SmemMapTC::total_floats * 4 + 128;
+constexpr size_t kSmemBytesTC = (size_t)SmemMapTC::total_floats * 4 + 256;
 
 template <bool SR16, int RM, typename S>
 __global__ void __launch_bounds__(kThreads, 1) svad_fused_tc(TileArgs a, int ntiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* sm = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SmemMapTC::total_floats * 4);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2);
-    GpuEnvTC<SR16> env{sm, bars, bars + kTcStages, bars + 2 * kTcStages, a.tape, (int)threadIdx.x, 0u, 0, 0, -1, -1, 0u, 0u};
+    constexpr int NB = TapeTC<SR16>::kBufs;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NB + 2);
+    GpuEnvTC<SR16> env{sm, bars, bars + NB, bars + 2 * NB, a.tape, (int)threadIdx.x, 0u, 0, 0, -2, 0u, 0u, 0u};
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; s++) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)) : "memory");                 // full: TMA
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(bars + kTcStages + s)) : "memory");     // consumed: 4 MMA warps
+        for (int s = 0; s < NB; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)) : "memory");          // landed: TMA
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + NB + s)) : "memory");     // consumed: the one MMA warp that reads it
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(bars + 2 * kTcStages)) : "memory");         // accumulators: 4 MMA warps
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(bars + 2 * NB)) : "memory");         // accumulators: 4 MMA warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if ((threadIdx.x >> 5) == kRingWarp) {   // the ring warp primes the weight ring
+    if ((threadIdx.x >> 5) == kRingWarp) {   // the ring warp primes every buffer whose first slab has no predecessor
         const int total = (int)((long)my_tiles * a.T * TapeTC<SR16>::nslab);
-        env.refill_upto(kTcStages - 1, total);
+        env.ring_freed(total);   // freed: -2 -> -1
     }
     if (threadIdx.x < 32) {   // warp 0 owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");

@@ -117,7 +117,8 @@ struct SmemMapTC {
     static constexpr int zre = e0;
     static constexpr int zim = e0 + kSlots * zpitch;
     static constexpr int lo0 = e0;                               // enc0 lo tiles [4][Kt][32] (after the STFT, before e0 is written)
-    static constexpr int lol = e0;                               // LSTM lo tiles [256][32]   (after enc1 has consumed e0)
+    static constexpr int lol_h = mag;                            // LSTM lo rows of h  [128][32] (over e1, dead once enc2 has run)
+    static constexpr int lol_x = e3 + 128 * kSlots;              // LSTM lo rows of e3 [128][32] (over enc1's partial-sum scratch)
     static constexpr int h = e0 + e0_floats;                     // 133632 B, atom aligned
     static constexpr int consts = h + kHid * kSlots;
     static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_bout = 1024, c_win = 1028;
@@ -129,7 +130,8 @@ struct SmemMapTC {
     static constexpr int stage_floats = kTcStageBytes / 4;
     static constexpr int total_floats = stage + kTcStages * stage_floats;
 };
-static_assert(SmemMapTC::e0 % 128 == 0 && SmemMapTC::h % 128 == 0 && SmemMapTC::e3 % 128 == 0, "atom alignment");
+static_assert(SmemMapTC::e0 % 256 == 0 && SmemMapTC::h % 128 == 0 && SmemMapTC::e3 % 128 == 0 && SmemMapTC::lol_x % 128 == 0, "atom / tile alignment");
+static_assert(SmemMapTC::lol_x + 128 * kSlots <= SmemMapTC::mag + SmemMapTC::mag_floats && SmemMapTC::e0_floats >= 4 * SmemMapTC::stage_floats, "LSTM-phase borrowings");
 static_assert(SmemMapTC::e0_floats >= 2 * kSlots * SmemMapTC::zpitch, "Z planes");
 static_assert((size_t)SmemMapTC::total_floats * 4 + 256 <= 232448, "shared memory budget");
 static_assert(SmemMap::e0_floats >= 4 * 128 * kSlots, "e0 region too small");

@@ -170,16 +170,36 @@ struct TapeTC {
     static constexpr int e0_nslab = (Kt / 32) * 3 * 2;   // (kc, tap) x {hi, lo}: 24 / 12
     static constexpr int e1_nslab = 8;                   // 16 channels x 192 floats
     static constexpr int e2_nslab = 2, e3_nslab = 2;     // 32 channels x 128 floats
-    static constexpr int l_nslab = 64;                   // (kc, gate block) x {hi, lo}
+    static constexpr int l_nslab = 32;                   // (kc, gate block): one 32 KB slab = tile pair {hi | lo}, read by ONE MMA warp
     static constexpr int e0_off = 0;
     static constexpr int e1_off = e0_off + e0_nslab * tile;
     static constexpr int e2_off = e1_off + 128 * 192;
     static constexpr int e3_off = e2_off + 64 * 128;
     static constexpr int l_off = e3_off + 64 * 128;
-    static constexpr int total = l_off + l_nslab * tile;
+    static constexpr int total = l_off + l_nslab * 2 * tile;
     static constexpr int nsimt = e1_nslab + e2_nslab + e3_nslab;
     static constexpr int nslab = e0_nslab + nsimt + l_nslab;
     SVAD_HD static constexpr bool is_mma(int i) { return i < e0_nslab || i >= e0_nslab + nsimt; }
+    // ---- slab -> shared-memory buffer.  Buffers 0-3 are the 4 x 16 KB ring (enc0 tiles, CUDA-core slabs).  Every bulk
+    // copy costs the same ~450 cycles of fixed latency up to 32 KB (tools/ubench_ingest.cu), so the LSTM streams 32 KB
+    // tile pairs through four double-size buffers: ring halves (ids 0, 2) and the e0 region, dead once enc1 has run
+    // (ids 4, 6).  dep_delta(idx) = how many slabs back the event lies that frees the buffer(s) of slab idx.
+    static constexpr int NA = e0_nslab + nsimt;          // slabs before the LSTM (a multiple of 4)
+    static constexpr int kBufs = 8;
+    SVAD_HD static constexpr int buf(int idx) { return idx < NA ? (idx & 3) : (((idx - NA) & 3) << 1); }
+    SVAD_HD static constexpr int dep_delta(int idx) {
+        if (idx < NA) return idx >= 4 ? 4 : (idx == 0 ? 4 : (idx == 3 ? 6 : 5));   // first slabs of a step wait for the last LSTM pairs
+        const int l = idx - NA;
+        return l >= 4 ? 4 : (l == 0 ? 3 : (l == 1 ? 2 : l + (nsimt - e1_nslab) + 1));
+    }
+    template <class M>
+    SVAD_HD static constexpr int buf_off(int b) { return (b & 4) ? M::e0 + (b & 3) * M::stage_floats : M::stage + b * M::stage_floats; }
+    // parity toggles a warp misses when it sits out an MMA phase: XOR of (1 << buf) over the phase's slabs
+    SVAD_HD static constexpr uint32_t phase_mask(int first, int count) {
+        uint32_t m = 0;
+        for (int i = 0; i < count; i++) m ^= 1u << buf(first + i);
+        return m;
+    }
     SVAD_HD static constexpr int slab_off(int i) {
         if (i < e0_nslab) return e0_off + i * tile;
         i -= e0_nslab;
@@ -189,13 +209,13 @@ struct TapeTC {
         i -= e2_nslab;
         if (i < e3_nslab) return e3_off + i * 32 * 128;
         i -= e3_nslab;
-        return l_off + i * tile;
+        return l_off + i * 2 * tile;
     }
     SVAD_HD static constexpr int slab_len(int i) {
         if (i < e0_nslab) return tile;
         i -= e0_nslab;
         if (i < e1_nslab) return 16 * 192;
-        return tile;   // enc2 / enc3 halves and LSTM tiles are all 4096 floats
+        return i < nsimt ? tile : 2 * tile;   // enc2 / enc3 halves: 4096 floats; LSTM: a tile pair
     }
 };
 

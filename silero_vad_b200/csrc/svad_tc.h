@@ -18,13 +18,14 @@
 //   tmem_ld16(lane_quarter, col, v)     16 consecutive columns of this thread's TMEM lane
 //   fence_async()                       make generic-proxy smem writes visible to the MMA (async proxy)
 //   tc_fence_before() / tc_fence_after()  order tcgen05.ld against later MMAs across a CTA barrier
-//   slab_wait(it)                       weight ring: wait until slab it has landed in its stage
-//   warp 0 only, executed by all its lanes with identical (warp-uniform) bookkeeping so that descriptors and
-//   counters stay in uniform registers; the single-lane work (TMA issue, MMA, commit) is elected inside:
-//     mark_free(it)     slab it was consumed by the CUDA cores (a CTA barrier has passed)
-//     free_upto(it)     wait until the MMAs reading every slab <= it have completed
-//     refill_upto(it)   issue the TMA copies of all not yet issued slabs <= it (slab i reuses the stage of i-4)
-//     mma_a(tile) / mma_b(rows)           descriptors; mma(col, adesc, ks, bdesc, ks, acc) issues one instruction
+//   slab_wait(idx) / slab_pass(idx)     weight ring: wait until slab idx (per-step index) has landed, returns its buffer / a warp
+//                                       that does not read the slab only keeps that buffer's parity bit in step
+//   skip_phase(mask, n)                 a warp that sat out an MMA phase fixes up its buffer parities
+//   ring warp only (all lanes, warp-uniform bookkeeping; the TMA issue is elected inside):
+//     wait_consumed_group(idx, 1)  the MMAs reading slab idx have completed (each slab has ONE consuming MMA warp, and the
+//                                  warps drift apart, so every slab is waited for individually, in order)
+//     ring_freed(total)   the next slab (in order) is consumed: advance and issue every slab whose buffer is now free
+//   MMA warps: mma_a(tile) / mma_b(rows, lbo) descriptors; mma(col, adesc, bdesc, ks, acc, ncols) issues one instruction
 #pragma once
 #include "svad_tile.h"
 
@@ -222,16 +223,16 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 env.tc_fence_after();
 #pragma unroll 1
                 for (int s = 0; s < TP::e0_nslab; s++) {
-                    const int is = it + s;
                     const int kc = s / 6, jo = (s >> 1) % 3, lo = s & 1;
                     const int j = (jo == 0) ? 1 : (jo == 1 ? 0 : 2);
+                    if (tc.warp != lo) { env.slab_pass(s); continue; }   // not this warp's slab: only keep the buffer parity in step
                     SVAD_CLK(c0);
-                    const float* tile = env.slab_wait(is);
+                    const float* tile = env.slab_wait(s);
                     SVAD_CLK(c1); SVAD_ACC(11, c1 - c0);
                     // warp 0 issues the w_hi slabs into D (TMEM columns 0..127), warp 1 the w_lo slabs into a second
                     // accumulator D2 (columns 256..383) so the two issue streams never touch the same accumulator;
                     // the epilogue adds them.
-                    if (tc.warp == lo) {
+                    {
                         const int f0 = (j == 2) ? 1 : 0, t0 = f0 + 1 - j, nf = (j == 1) ? 4 : 3;
                         const auto ad = env.mma_a(tile);
                         const auto bh = env.mma_b(sm + M::mag + (f0 * M::mag_pitch + kc * 32) * kSlots, M::mag_pitch * kSlots * 4);
@@ -246,18 +247,16 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                                 env.mma(256 + t0 * 32, ad, bh, ks, !first, 32 * nf);   // w_lo * x_hi
                             }
                         }
-                        env.mma_slab_done(is);
-                    } else {
-                        env.slab_skip(is);
+                        env.mma_slab_done(s);
                     }
                 }
                 env.acc_commit();
                 SVAD_STAMP(3);
-            } else if (tc.warp == kRingWarp) {   // ring manager: as each slab is released, issue the next pending one
+            } else {
+                env.skip_phase(TP::phase_mask(0, TP::e0_nslab), TP::e0_nslab);
+                if (tc.warp == kRingWarp) {   // ring manager: as each slab is released, issue whatever its buffer unblocks
 #pragma unroll 1
-                for (int s = 0; s < TP::e0_nslab; s++) {
-                    env.free_upto(it + s);
-                    env.refill_upto(it + s + kTcStages, total_slabs);
+                    for (int s = 0; s < TP::e0_nslab; s++) { env.wait_consumed_group(s, 1); env.ring_freed(total_slabs); }
                 }
             }
             it += TP::e0_nslab;
@@ -300,37 +299,37 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
 #pragma unroll 1
             for (int s = 0; s < TP::e1_nslab; s++, it++) {
                 SVAD_CLK(w0);
-                const float* slab = env.slab_wait(it);
+                const float* slab = env.slab_wait(TP::e0_nslab + s);
                 SVAD_CLK(w1); SVAD_ACC(18, w1 - w0);
                 enc1_slab<RM, M>(tc, sm, slab, rg, s * 16, s * 16 + 16);
                 if (s == TP::e1_nslab - 1) enc1_park<RM, M>(tc, sm, rg);
                 SVAD_CLK(w2); SVAD_ACC(19, w2 - w1);
                 env.sync();
                 SVAD_CLK(w3); SVAD_ACC(20, w3 - w2);
-                if (tc.warp == kRingWarp) { env.mark_free(it); env.refill_upto(it + kTcStages, total_slabs); }
+                if (tc.warp == kRingWarp) env.ring_freed(total_slabs);
             }
             enc1_store<RM, M>(tc, sm, rg);
             env.sync();
             SVAD_STAMP(21);
 #pragma unroll 1
             for (int s = 0; s < 2; s++, it++) {
-                const float* slab = env.slab_wait(it);
+                const float* slab = env.slab_wait(TP::e0_nslab + TP::e1_nslab + s);
                 enc2_slab_tc<RM, M>(tc, sm, slab, rg, s * 32, s == 0, s == 1);
                 env.sync();
-                if (tc.warp == kRingWarp) { env.mark_free(it); env.refill_upto(it + kTcStages, total_slabs); }
+                if (tc.warp == kRingWarp) env.ring_freed(total_slabs);
             }
             SVAD_STAMP(22);
 #pragma unroll 1
             for (int s = 0; s < 2; s++, it++) {
-                const float* slab = env.slab_wait(it);
+                const float* slab = env.slab_wait(TP::e0_nslab + TP::e1_nslab + 2 + s);
                 enc3_slab_tc<RM, M>(tc, sm, slab, rg, s * 32, s == 0, s == 1);
-                if (s == 1) stage_lo(tc.tid, sm + M::h, sm + M::lol + kHid * kSlots, kHid);   // h is from the previous step
+                if (s == 1) stage_lo(tc.tid, sm + M::h, sm + M::lol_h, kHid);   // h is from the previous step; e1 (underneath) is dead
                 env.sync();
-                if (tc.warp == kRingWarp) { env.mark_free(it); env.refill_upto(it + kTcStages, total_slabs); }
+                if (tc.warp == kRingWarp) env.ring_freed(total_slabs);
             }
             SVAD_STAMP(6);
             // ---------------- LSTM on the tensor core: gates[m*128 + j][slot] = sum_k W[.][k] * [e3 ; h][k][slot]
-            stage_lo(tc.tid, sm + M::e3, sm + M::lol, kHid);
+            stage_lo(tc.tid, sm + M::e3, sm + M::lol_x, kHid);
             env.fence_async();
             env.sync();
             SVAD_STAMP(7);
@@ -338,42 +337,30 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 env.tc_fence_after();
 #pragma unroll 1
                 for (int s = 0; s < TP::l_nslab; s++) {
-                    const int is = it + s;
-                    const int kc = s >> 3, m = (s >> 1) & 3, lo = s & 1;
+                    const int kc = s >> 2, m = s & 3;
+                    if (m != tc.warp) { env.slab_pass(TP::NA + s); continue; }
                     SVAD_CLK(c0);
-                    const float* tile = env.slab_wait(is);
+                    const float* tile = env.slab_wait(TP::NA + s);
                     SVAD_CLK(c1); SVAD_ACC(13, c1 - c0);
-                    if (m == tc.warp) {
-                        SVAD_CLK(d0);
-                        const auto ad = env.mma_a(tile);
-                        const auto bh = env.mma_b((kc < 4) ? sm + M::e3 + kc * 32 * kSlots : sm + M::h + (kc - 4) * 32 * kSlots, 4096);
-                        const auto bl = env.mma_b(sm + M::lol + kc * 32 * kSlots, 4096);
+                    const auto ah = env.mma_a(tile), al = env.mma_a(tile + TP::tile);
+                    const auto bh = env.mma_b((kc < 4) ? sm + M::e3 + kc * 32 * kSlots : sm + M::h + (kc - 4) * 32 * kSlots, 4096);
+                    const auto bl = env.mma_b((kc < 4) ? sm + M::lol_x + kc * 32 * kSlots : sm + M::lol_h + (kc - 4) * 32 * kSlots, 4096);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            if (!lo) {
-                                const bool first = (kc == 0) && (ks == 0);
-                                env.mma(128 + m * 32, ad, bh, ks, !first, 32);
-                                env.mma(128 + m * 32, ad, bl, ks, true, 32);
-                            } else {
-                                env.mma(128 + m * 32, ad, bh, ks, true, 32);
-                            }
-                        }
-                        SVAD_CLK(d1); SVAD_ACC(15, d1 - d0);
-                        env.mma_slab_done(is);
-                        SVAD_CLK(d2); SVAD_ACC(16, d2 - d1);
-                    } else {
-                        SVAD_CLK(d3);
-                        env.slab_skip(is);
-                        SVAD_CLK(d4); SVAD_ACC(17, d4 - d3);
+                    for (int ks = 0; ks < 4; ks++) {
+                        const bool first = (kc == 0) && (ks == 0);
+                        env.mma(128 + m * 32, ah, bh, ks, !first, 32);   // w_hi * x_hi
+                        env.mma(128 + m * 32, ah, bl, ks, true, 32);     // w_hi * x_lo
+                        env.mma(128 + m * 32, al, bh, ks, true, 32);     // w_lo * x_hi
                     }
+                    env.mma_slab_done(TP::NA + s);
                 }
                 env.acc_commit();
                 SVAD_STAMP(8);
-            } else if (tc.warp == kRingWarp) {
+            } else {
+                env.skip_phase(TP::phase_mask(TP::NA, TP::l_nslab), TP::l_nslab);
+                if (tc.warp == kRingWarp) {
 #pragma unroll 1
-                for (int s = 0; s < TP::l_nslab; s++) {
-                    env.free_upto(it + s);
-                    env.refill_upto(it + s + kTcStages, total_slabs);
+                    for (int s = 0; s < TP::l_nslab; s++) { env.wait_consumed_group(TP::NA + s, 1); env.ring_freed(total_slabs); }
                 }
             }
             it += TP::l_nslab;

@@ -105,26 +105,27 @@ struct EmuEnvTC {
     void tc_fence_before() {}
     void tc_fence_after() {}
     bool lane0() const { return (tid_ & 31) == 0; }
-    void issue(int it) {
-        const int idx = it % TapeTC<SR16>::nslab, stage = it % kTcStages;
-        memcpy(sh->smem.data() + SmemMapTC::stage + stage * SmemMapTC::stage_floats, sh->tape + TapeTC<SR16>::slab_off(idx),
-               sizeof(float) * TapeTC<SR16>::slab_len(idx));
+    using TP = TapeTC<SR16>;
+    int issued_idx = 0, seen = 0;   // ring-warp: per-step index of the next slab to issue; consumers: global index of the next slab to wait for
+    void issue(int idx) {
+        memcpy(sh->smem.data() + TP::template buf_off<SmemMapTC>(TP::buf(idx)), sh->tape + TP::slab_off(idx), sizeof(float) * TP::slab_len(idx));
     }
-    const float* slab_wait(int it) {
-        while (sh->landed.load(std::memory_order_acquire) <= it) sched_yield();
-        return sh->smem.data() + SmemMapTC::stage + (it % kTcStages) * SmemMapTC::stage_floats;
+    const float* slab_wait(int idx) {
+        while (sh->landed.load(std::memory_order_acquire) <= seen) sched_yield();
+        seen++;
+        return sh->smem.data() + TP::template buf_off<SmemMapTC>(TP::buf(idx));
     }
-    void mark_free(int x) { freed = x; }
-    void free_upto(int x) {
-        for (int y = freed + 1; y <= x; y++)
-            if (TapeTC<SR16>::is_mma(y % TapeTC<SR16>::nslab))
-                while (sh->released[y].load(std::memory_order_acquire) < 4) sched_yield();
-        if (x > freed) freed = x;
+    void skip_phase(uint32_t, int n) { seen += n; }
+    void slab_pass(int) { seen++; }
+    void wait_consumed_group(int, int n) {   // the next n slabs to be freed are MMA slabs: wait for the consumer's arrival on the last
+        while (sh->released[freed + n].load(std::memory_order_acquire) < 1) sched_yield();
     }
-    void refill_upto(int x, int total) {
-        while (issued <= x && issued < total) {
-            if (lane0()) { issue(issued); sh->landed.store(issued + 1, std::memory_order_release); }
+    void ring_freed(int total) {
+        freed++;
+        while (issued < total && issued - TP::dep_delta(issued_idx) <= freed) {
+            if (lane0()) { issue(issued_idx); sh->landed.store(issued + 1, std::memory_order_release); }
             issued++;
+            if (++issued_idx == TP::nslab) issued_idx = 0;
         }
     }
     struct BDesc { const float* rows; int lbo_floats; };
@@ -148,8 +149,8 @@ struct EmuEnvTC {
             }
         }
     }
-    void mma_slab_done(int it) { if (lane0()) sh->released[it].fetch_add(1, std::memory_order_acq_rel); }
-    void slab_skip(int it) { if (lane0()) sh->released[it].fetch_add(1, std::memory_order_acq_rel); }
+    void mma_slab_done(int) { if (lane0()) sh->released[seen - 1].fetch_add(1, std::memory_order_acq_rel); }
+    void slab_skip(int) { if (lane0()) sh->released[seen - 1].fetch_add(1, std::memory_order_acq_rel); }
     void acc_commit() {}
     void acc_wait() { pthread_barrier_wait(&sh->bar); }
     void tmem_ld16(int lq, int col, float (&v)[16]) {
@@ -168,17 +169,14 @@ void run_tc(const TileArgs& a, int ntiles) {
     const int total = (int)((long)ntiles * a.T * TapeTC<SR16>::nslab);
     sh.released.reset(new std::atomic<int>[total + 1]);
     for (int i = 0; i <= total; i++) sh.released[i] = 0;
-    int pre = 0;
-    {
-        EmuEnvTC<SR16> e0{&sh, 0};
-        for (int i = 0; i < kTcStages && i < total; i++) { e0.issue(i); pre = i + 1; }
-        sh.landed = pre;
-    }
+    EmuEnvTC<SR16> boot{&sh, 0};
+    boot.freed = -2;
+    boot.ring_freed(total);   // freed = -1: primes every buffer whose first slab has no predecessor
     std::vector<std::thread> th;
     for (int t = 0; t < kThreads; t++)
         th.emplace_back([&, t] {
             EmuEnvTC<SR16> env{&sh, t};
-            env.issued = pre;   // (only the ring warp uses it)
+            env.issued = boot.issued; env.issued_idx = boot.issued_idx; env.freed = -1;
             run_cta_tc<SR16, RM, S>(env, a, 0, 1, ntiles);
         });
     for (auto& x : th) x.join();

@@ -8,7 +8,13 @@
 #include <vector>
 namespace cg = cooperative_groups;
 
-constexpr int kStage = 32768, kStages = 4;
+#ifndef KSTAGE
+#define KSTAGE 32768
+#endif
+#ifndef KSTAGES
+#define KSTAGES 4
+#endif
+constexpr int kStage = KSTAGE, kStages = KSTAGES;
 
 __device__ __forceinline__ uint32_t su32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -89,9 +95,7 @@ int main() {
     const int bytes = 1792 * 1024;   // ~ hi+lo weight tape of the 16 kHz branch
     char* tape; cudaMalloc(&tape, bytes); cudaMemset(tape, 0, bytes);
     printf("%s, %d SMs, tape %d KB\n", p.name, p.multiProcessorCount, bytes / 1024);
+    printf("stage %d B x %d stages\n", kStage, kStages);
     run<1>(tape, bytes, p.multiProcessorCount);
-    run<2>(tape, bytes, p.multiProcessorCount);
-    run<4>(tape, bytes, p.multiProcessorCount);
-    run<8>(tape, bytes, p.multiProcessorCount);
     return 0;
 }
