@@ -196,10 +196,11 @@ struct GpuEnvTC {
     __device__ __forceinline__ uint64_t mma_a(const float* tile) const { return umma_desc(smem_u32(tile), 16, 1024, 2); }
     // B: N atoms of 32 slots (consecutive frames for enc0) at stride lbo_bytes, 4-row k groups 512 B apart
     __device__ __forceinline__ uint64_t mma_b(const float* rows, int lbo_bytes) const { return umma_desc(smem_u32(rows), (uint32_t)lbo_bytes, 512, 1); }
+    template <int MM = 128>
     __device__ __forceinline__ void mma(int col, uint64_t ad, uint64_t bd, int ks, bool acc, int ncols) {
         const uint64_t a2 = ad + (uint64_t)(ks * 2), b2 = bd + (uint64_t)(ks * 64);
         const uint32_t accf = acc ? 1u : 0u;
-        const uint32_t idesc = (kIdescTf32 & ~(0x3Fu << 17)) | ((uint32_t)(ncols >> 3) << 17);
+        const uint32_t idesc = (kIdescTf32 & ~((0x3Fu << 17) | (0x1Fu << 24))) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
         if (elect())
             asm volatile(
                 "{\n"

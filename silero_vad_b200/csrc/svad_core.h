@@ -117,6 +117,7 @@ struct SmemMapTC {
     static constexpr int zre = e0;
     static constexpr int zim = e0 + kSlots * zpitch;
     static constexpr int lo0 = e0;                               // enc0 lo tiles [4][Kt][32] (after the STFT, before e0 is written)
+    static constexpr int e0lo = mag;                             // lo parts of e0 [4][128][32] (enc1's second B operand; mag is dead by then)
     static constexpr int lol_h = mag;                            // LSTM lo rows of h  [128][32] (over e1, dead once enc2 has run)
     static constexpr int lol_x = e3 + 128 * kSlots;              // LSTM lo rows of e3 [128][32] (over enc1's partial-sum scratch)
     static constexpr int h = e0 + e0_floats;                     // 133632 B, atom aligned
@@ -124,7 +125,8 @@ struct SmemMapTC {
     static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_bout = 1024, c_win = 1028;
     static constexpr int c_twr = c_win + 256, c_twi = c_twr + 256;
     static constexpr int c_wnyq = c_twi + 256;                   // enc0 weights of the Nyquist bin: [3 taps][128]
-    static constexpr int consts_floats = c_wnyq + 384;
+    static constexpr int c_nyq = c_wnyq + 384;                   // |X| of the Nyquist bin, [4 frames][32 slots] (copied out of mag before e0lo overwrites it)
+    static constexpr int consts_floats = c_nyq + 4 * kSlots;
     static constexpr int headp = consts + consts_floats;
     static constexpr int stage = (headp + kSlots + 255) / 256 * 256;   // 1 KB aligned
     static constexpr int stage_floats = kTcStageBytes / 4;

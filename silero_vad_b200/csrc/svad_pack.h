@@ -168,29 +168,28 @@ struct TapeTC {
     static constexpr int Kt = G::F - 1;                  // 128 / 64 bins on the tensor core
     static constexpr int tile = 128 * 32;                // floats per [128 x 32] tile = one 16 KB slab
     static constexpr int e0_nslab = (Kt / 32) * 3 * 2;   // (kc, tap) x {hi, lo}: 24 / 12
-    static constexpr int e1_nslab = 8;                   // 16 channels x 192 floats
+    static constexpr int e1_nslab = 12;                  // (tap, kc): [64 x 32] tiles {hi | lo} = 16 KB, read by MMA warp kc
     static constexpr int e2_nslab = 2, e3_nslab = 2;     // 32 channels x 128 floats
     static constexpr int l_nslab = 32;                   // (kc, gate block): one 32 KB slab = tile pair {hi | lo}, read by ONE MMA warp
     static constexpr int e0_off = 0;
     static constexpr int e1_off = e0_off + e0_nslab * tile;
-    static constexpr int e2_off = e1_off + 128 * 192;
+    static constexpr int e2_off = e1_off + e1_nslab * tile;
     static constexpr int e3_off = e2_off + 64 * 128;
     static constexpr int l_off = e3_off + 64 * 128;
     static constexpr int total = l_off + l_nslab * 2 * tile;
-    static constexpr int nsimt = e1_nslab + e2_nslab + e3_nslab;
-    static constexpr int nslab = e0_nslab + nsimt + l_nslab;
-    SVAD_HD static constexpr bool is_mma(int i) { return i < e0_nslab || i >= e0_nslab + nsimt; }
+    static constexpr int nsimt = e2_nslab + e3_nslab;    // slabs read by the CUDA cores
+    static constexpr int nslab = e0_nslab + e1_nslab + nsimt + l_nslab;
     // ---- slab -> shared-memory buffer.  Buffers 0-3 are the 4 x 16 KB ring (enc0 tiles, CUDA-core slabs).  Every bulk
     // copy costs the same ~450 cycles of fixed latency up to 32 KB (tools/ubench_ingest.cu), so the LSTM streams 32 KB
     // tile pairs through four double-size buffers: ring halves (ids 0, 2) and the e0 region, dead once enc1 has run
     // (ids 4, 6).  dep_delta(idx) = how many slabs back the event lies that frees the buffer(s) of slab idx.
-    static constexpr int NA = e0_nslab + nsimt;          // slabs before the LSTM (a multiple of 4)
+    static constexpr int NA = e0_nslab + e1_nslab + nsimt;   // slabs before the LSTM (a multiple of 4)
     static constexpr int kBufs = 8;
     SVAD_HD static constexpr int buf(int idx) { return idx < NA ? (idx & 3) : (((idx - NA) & 3) << 1); }
     SVAD_HD static constexpr int dep_delta(int idx) {
         if (idx < NA) return idx >= 4 ? 4 : (idx == 0 ? 4 : (idx == 3 ? 6 : 5));   // first slabs of a step wait for the last LSTM pairs
         const int l = idx - NA;
-        return l >= 4 ? 4 : (l == 0 ? 3 : (l == 1 ? 2 : l + (nsimt - e1_nslab) + 1));
+        return l >= 4 ? 4 : (l == 0 ? 3 : (l == 1 ? 2 : l + nsimt + 1));   // pairs 2, 3 sit in the e0 region: free once the last enc1 slab is consumed
     }
     template <class M>
     SVAD_HD static constexpr int buf_off(int b) { return (b & 4) ? M::e0 + (b & 3) * M::stage_floats : M::stage + b * M::stage_floats; }
@@ -203,7 +202,7 @@ struct TapeTC {
     SVAD_HD static constexpr int slab_off(int i) {
         if (i < e0_nslab) return e0_off + i * tile;
         i -= e0_nslab;
-        if (i < e1_nslab) return e1_off + i * 16 * 192;
+        if (i < e1_nslab) return e1_off + i * tile;
         i -= e1_nslab;
         if (i < e2_nslab) return e2_off + i * 32 * 128;
         i -= e2_nslab;
@@ -214,8 +213,7 @@ struct TapeTC {
     SVAD_HD static constexpr int slab_len(int i) {
         if (i < e0_nslab) return tile;
         i -= e0_nslab;
-        if (i < e1_nslab) return 16 * 192;
-        return i < nsimt ? tile : 2 * tile;   // enc2 / enc3 halves: 4096 floats; LSTM: a tile pair
+        return i < e1_nslab + nsimt ? tile : 2 * tile;   // enc1 tile pairs, enc2 / enc3 halves: 4096 floats; LSTM: a [128 x 32] tile pair
     }
 };
 
@@ -229,6 +227,17 @@ inline void pack_umma_a(const float* A, long lda, long ldk, float* dst) {
             const int pos = (r / 8) * 256 + (r % 8) * 32 + (((k / 4) ^ (r % 8)) * 4) + (k % 4);
             dst[pos] = v;
             dst[128 * 32 + pos] = v - trunc_tf32(v);
+        }
+}
+
+// A[r][k] (r < 64, k < 32) -> K-major SWIZZLE_128B half tile pair {hi | lo}, 2048 floats each (M = 64 instructions)
+inline void pack_umma_a64(const float* A, long lda, long ldk, float* dst) {
+    for (int r = 0; r < 64; r++)
+        for (int k = 0; k < 32; k++) {
+            const float v = A[r * lda + k * ldk];
+            const int pos = (r / 8) * 256 + (r % 8) * 32 + (((k / 4) ^ (r % 8)) * 4) + (k % 4);
+            dst[pos] = v;
+            dst[64 * 32 + pos] = v - trunc_tf32(v);
         }
 }
 
@@ -252,7 +261,12 @@ inline bool pack_branch_tc(const TensorMap& tm, PackedBranch& out, std::string& 
             const int j = jo == 0 ? 1 : (jo == 1 ? 0 : 2);
             pack_umma_a(w0 + (size_t)(kc * 32) * 3 + j, (long)G::F * 3, 3, t + T::e0_off + (kc * 3 + jo) * 2 * T::tile);   // {hi | lo} = 2 slabs
         }
-    memcpy(t + T::e1_off, v1.tape.data() + T1::e1_off, sizeof(float) * (T1::l_off - T1::e1_off));   // enc1..enc3 unchanged
+    const float* w1 = tm.at(p + "encoder.1.reparam_conv.weight").data.data();   // [64][128][3]
+    for (int jo = 0; jo < 3; jo++) {   // tap order 1, 2, 0: the first slab of every MMA warp covers both output frames
+        const int j = jo == 2 ? 0 : jo + 1;
+        for (int kc = 0; kc < 4; kc++) pack_umma_a64(w1 + (size_t)(kc * 32) * 3 + j, 128 * 3, 3, t + T::e1_off + (jo * 4 + kc) * T::tile);
+    }
+    memcpy(t + T::e2_off, v1.tape.data() + T1::e2_off, sizeof(float) * (T1::l_off - T1::e2_off));   // enc2, enc3 as in the fp32 tape
     for (int kc = 0; kc < 8; kc++)
         for (int m = 0; m < 4; m++) {
             const float* src = (kc < 4 ? wih : whh) + (size_t)(m * 128) * 128 + (kc & 3) * 32;

@@ -211,6 +211,8 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
             // lo rows of mag[f][0..Kt) -> lo0[f][0..Kt)  (the Z planes there are dead now)
 #pragma unroll
             for (int f = 0; f < 4; f++) stage_lo(tc.tid, sm + M::mag + f * M::mag_pitch * kSlots, sm + M::lo0 + f * Kt * kSlots, Kt);
+            if (tc.tid < 4 * kSlots)   // row Kt of every frame (identity swizzle): the Nyquist bin, used by the enc0 epilogue
+                sm[M::consts + M::c_nyq + tc.tid] = sm[M::mag + (M::mag_pitch * (tc.tid >> 5) + Kt) * kSlots + (tc.tid & 31)];
             env.fence_async();
             env.tc_fence_before();     // the previous step's tcgen05.ld of these TMEM columns are done
             env.sync();
@@ -276,39 +278,93 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     env.tmem_ld16(lq, tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v + 16));
                     env.tmem_ld16(lq, 256 + tt * 32, *reinterpret_cast<float(*)[16]>(v2));
                     env.tmem_ld16(lq, 256 + tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v2 + 16));
-                    const float* nyq = sm + M::mag + (M::mag_pitch * tt + Kt) * kSlots;   // row Kt of frame tt (identity swizzle)
+                    const float* nyq = sm + M::consts + M::c_nyq + tt * kSlots;
+                    float lo[32];
 #pragma unroll
                     for (int s = 0; s < 32; s++) {
                         float acc = (v[s] + v2[s]) + b0;
-                        if (tt > 0) acc = fmaf(wn0, nyq[s - M::mag_pitch * kSlots], acc);
+                        if (tt > 0) acc = fmaf(wn0, nyq[s - kSlots], acc);
                         acc = fmaf(wn1, nyq[s], acc);
-                        if (tt < 3) acc = fmaf(wn2, nyq[s + M::mag_pitch * kSlots], acc);
+                        if (tt < 3) acc = fmaf(wn2, nyq[s + kSlots], acc);
                         v[s] = relu(acc);
+                        lo[s] = lo_part(v[s]);
                     }
+                    // e0 (hi = as is) and its lo parts, both as tcgen05 B rows: enc1 runs on the tensor core too
                     float* dst = sm + M::e0 + (tt * 128 + row) * kSlots;
+                    float* dlo = sm + M::e0lo + (tt * 128 + row) * kSlots;
 #pragma unroll
-                    for (int gq = 0; gq < 8; gq++)
-                        *reinterpret_cast<f4*>(dst + ((gq ^ key_hi(row)) << 2)) = f4{v[4 * gq], v[4 * gq + 1], v[4 * gq + 2], v[4 * gq + 3]};
+                    for (int gq = 0; gq < 8; gq++) {
+                        const int pq = tc_f4(gq, row) << 2;
+                        *reinterpret_cast<f4*>(dst + pq) = f4{v[4 * gq], v[4 * gq + 1], v[4 * gq + 2], v[4 * gq + 3]};
+                        *reinterpret_cast<f4*>(dlo + pq) = f4{lo[4 * gq], lo[4 * gq + 1], lo[4 * gq + 2], lo[4 * gq + 3]};
+                    }
                 }
             }
+            env.fence_async();
             env.tc_fence_before();
             env.sync();
             SVAD_STAMP(5);
-            // ---------------- enc1..enc3 on the CUDA cores (as in the fp32 kernel)
-            enc1_init<RM, M>(tc, sm, rg);
+            // ---------------- enc1 on the tensor core: M = 64 output channels, N = 2 output frames x 32 slots, K = 3 taps x 128.
+            // out[tt] = sum_j W_j e0[2tt - 1 + j]: tap 1 reads frames (0, 2), tap 2 frames (1, 3) (N = 64, LBO = 2 frames), tap 0
+            // frame 1 for tt = 1 only (N = 32; frame -1 is the zero padding).  MMA warp w owns k-chunk w of every tap and its own
+            // accumulator (64 TMEM columns; enc0's are free again), so the four issue streams never serialise on one accumulator.
+            if (tc.warp < 4) {
+                env.tc_fence_after();
+                const int abase = (tc.warp & 1) * 64 + (tc.warp >> 1) * 256;
 #pragma unroll 1
-            for (int s = 0; s < TP::e1_nslab; s++, it++) {
-                SVAD_CLK(w0);
-                const float* slab = env.slab_wait(TP::e0_nslab + s);
-                SVAD_CLK(w1); SVAD_ACC(18, w1 - w0);
-                enc1_slab<RM, M>(tc, sm, slab, rg, s * 16, s * 16 + 16);
-                if (s == TP::e1_nslab - 1) enc1_park<RM, M>(tc, sm, rg);
-                SVAD_CLK(w2); SVAD_ACC(19, w2 - w1);
-                env.sync();
-                SVAD_CLK(w3); SVAD_ACC(20, w3 - w2);
-                if (tc.warp == kRingWarp) env.ring_freed(total_slabs);
+                for (int s = 0; s < TP::e1_nslab; s++) {
+                    const int jo = s >> 2, kc = s & 3;
+                    if (kc != tc.warp) { env.slab_pass(TP::e0_nslab + s); continue; }
+                    const float* tile = env.slab_wait(TP::e0_nslab + s);
+                    const int f0 = (jo == 0) ? 0 : 1, ncols = (jo == 2) ? 32 : 64, col = abase + ((jo == 2) ? 32 : 0);
+                    const auto ah = env.mma_a(tile), al = env.mma_a(tile + 64 * 32);
+                    const auto bh = env.mma_b(sm + M::e0 + (f0 * 128 + kc * 32) * kSlots, 2 * 128 * kSlots * 4);
+                    const auto bl = env.mma_b(sm + M::e0lo + (f0 * 128 + kc * 32) * kSlots, 2 * 128 * kSlots * 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const bool first = (jo == 0) && (ks == 0);
+                        env.template mma<64>(col, ah, bh, ks, !first, ncols);
+                        env.template mma<64>(col, ah, bl, ks, true, ncols);
+                        env.template mma<64>(col, al, bh, ks, true, ncols);
+                    }
+                    env.mma_slab_done(TP::e0_nslab + s);
+                }
+                env.acc_commit();
+            } else {
+                env.skip_phase(TP::phase_mask(TP::e0_nslab, TP::e1_nslab), TP::e1_nslab);
+                if (tc.warp == kRingWarp) {
+#pragma unroll 1
+                    for (int s = 0; s < TP::e1_nslab; s++) { env.wait_consumed_group(TP::e0_nslab + s, 1); env.ring_freed(total_slabs); }
+                }
             }
-            enc1_store<RM, M>(tc, sm, rg);
+            it += TP::e1_nslab;
+            env.acc_wait();
+            SVAD_STAMP(20);
+            // epilogue: an M = 64 accumulator keeps row r in TMEM lane 32 * (r / 16) + r % 16, so lanes 0-15 of every warp hold
+            // channel 16 * lq + lane; warps w and w + 4 take output frame 0 / 1.  Sum the four accumulators, + bias, ReLU -> e1
+            {
+                float v[32], p[32];
+                const int o = 16 * lq + (tc.lane & 15), tt = half;
+                env.tmem_ld16(lq, tt * 32, *reinterpret_cast<float(*)[16]>(v));
+                env.tmem_ld16(lq, tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v + 16));
+#pragma unroll
+                for (int w = 1; w < 4; w++) {
+                    const int ab = (w & 1) * 64 + (w >> 1) * 256;
+                    env.tmem_ld16(lq, ab + tt * 32, *reinterpret_cast<float(*)[16]>(p));
+                    env.tmem_ld16(lq, ab + tt * 32 + 16, *reinterpret_cast<float(*)[16]>(p + 16));
+#pragma unroll
+                    for (int s = 0; s < 32; s++) v[s] += p[s];
+                }
+                if (tc.lane < 16) {
+                    const float b1 = sm[M::consts + M::c_b1 + o];
+                    float* dst = sm + M::e1 + (tt * 64 + o) * kSlots;
+#pragma unroll
+                    for (int gq = 0; gq < 8; gq++)
+                        *reinterpret_cast<f4*>(dst + ((gq ^ key_lo(o)) << 2)) =
+                            f4{relu(v[4 * gq] + b1), relu(v[4 * gq + 1] + b1), relu(v[4 * gq + 2] + b1), relu(v[4 * gq + 3] + b1)};
+                }
+            }
+            env.tc_fence_before();
             env.sync();
             SVAD_STAMP(21);
 #pragma unroll 1

@@ -131,9 +131,11 @@ struct EmuEnvTC {
     struct BDesc { const float* rows; int lbo_floats; };
     const float* mma_a(const float* tile) { return tile; }
     BDesc mma_b(const float* rows, int lbo_bytes) { return BDesc{rows, lbo_bytes / 4}; }
+    template <int MM = 128>
     void mma(int col, const float* a_tile, BDesc b, int ks, bool acc, int ncols) {
         if (!lane0()) return;
-        for (int r = 0; r < 128; r++) {
+        for (int r = 0; r < MM; r++) {
+            const int dlane = (MM == 64) ? 32 * (r / 16) + r % 16 : r;   // M = 64: lanes 0-15 of every subpartition
             for (int n = 0; n < ncols; n++) {
                 const float* b_rows = b.rows + (n >> 5) * b.lbo_floats + ks * 8 * 32;   // N atom n/32 at stride LBO
                 const int nn = n & 31;
@@ -144,7 +146,7 @@ struct EmuEnvTC {
                     const float bv = b_rows[kk * 32 + ((((nn >> 3) ^ (kk & 3)) << 3) | (nn & 7))];   // rows start at a multiple of 8: (row & 3) == (kk & 3)
                     s += (double)tf32_trunc(av) * (double)tf32_trunc(bv);
                 }
-                float& d = sh->tmem[r * 512 + col + n];
+                float& d = sh->tmem[dlane * 512 + col + n];
                 d = (acc ? d : 0.0f) + (float)s;
             }
         }

@@ -22,12 +22,11 @@ dbg.zero_()
 m.engine.forward_device(16000, B, 512 * T, 512 * T, x.data_ptr(), 0, 0, 0, 0, p.data_ptr(), T, torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 d = dbg.cpu().tolist()
-names = ["STFT", "lo-stage enc0 + sync", "enc0 MMA issue loop", "enc0 MMA tail (acc_wait)", "enc0 epilogue", "enc1-3 (CUDA cores)", "lo-stage LSTM + sync",
+names = ["STFT", "lo-stage enc0 + sync", "enc0 MMA issue loop", "enc0 MMA tail (acc_wait)", "enc0 epilogue", "enc1 (MMA) + enc2-3 (CUDA cores)", "lo-stage LSTM + sync",
          "LSTM MMA issue loop", "LSTM MMA tail", "LSTM epilogue + head"]
 tot = d[10] - d[0]
 for i, n in enumerate(names):
     print(f"{n:28s} {d[i+1]-d[i]:8d} cycles  {100*(d[i+1]-d[i])/tot:5.1f}%")
 print(f"{'step total':28s} {tot:8d} cycles")
 print(f"enc0 loop: slab_wait {d[11]} cycles, free_upto {d[12]} cycles;  LSTM loop: slab_wait {d[13]}, free_upto {d[14]}")
-print(f"LSTM warp0: MMA blocks (16 slabs, 96 MMAs) {d[15]} cycles, commits {d[16]}, skips (48) {d[17]}")
-print(f"enc1: {d[21]-d[5]} cycles total; tid0 slab_wait {d[18]}, compute {d[19]}, sync {d[20]};  enc2: {d[22]-d[21]};  enc3: {d[6]-d[22]}")
+print(f"enc1 MMA phase: {d[20]-d[5]} cycles, epilogue {d[21]-d[20]};  enc2: {d[22]-d[21]};  enc3: {d[6]-d[22]}")
