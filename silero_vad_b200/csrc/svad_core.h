@@ -22,8 +22,10 @@
 
 #if defined(__CUDACC__)
 #define SVAD_HD __host__ __device__ __forceinline__
+#define SVAD_COLD __host__ __device__ __noinline__
 #else
 #define SVAD_HD inline
+#define SVAD_COLD inline
 #endif
 
 namespace svad {
@@ -108,9 +110,12 @@ struct SmemMapTC {
     static constexpr int mag_pitch = 132;                        // rows per frame
     static constexpr int mag = 0;
     static constexpr int mag_floats = 4 * mag_pitch * kSlots;    // 16896 floats = 132 x 512 B
-    static constexpr int e1 = mag;
-    static constexpr int e2 = e1 + 2 * 64 * kSlots;
-    static constexpr int e3 = e2 + 64 * kSlots;                  // 24576 B, atom aligned
+    // activations after enc0 (all as tcgen05 B rows; hi = the fp32 value, lo = its tf32 truncation error), over the dead mag rows
+    static constexpr int e1 = mag;                               // [2][64][32]
+    static constexpr int e1lo = e1 + 2 * 64 * kSlots;
+    static constexpr int e2 = e1lo + 2 * 64 * kSlots;            // [64][32]
+    static constexpr int e2lo = e2 + 64 * kSlots;
+    static constexpr int e3 = e2lo + 64 * kSlots;                // [128][32]
     static constexpr int e0 = mag + mag_floats;
     static constexpr int zpitch = 257;
     static constexpr int e0_floats = 129 * 128;                  // 66048 B >= Z planes (2*32*257) and e0 (4*128*32)
@@ -118,8 +123,8 @@ struct SmemMapTC {
     static constexpr int zim = e0 + kSlots * zpitch;
     static constexpr int lo0 = e0;                               // enc0 lo tiles [4][Kt][32] (after the STFT, before e0 is written)
     static constexpr int e0lo = mag;                             // lo parts of e0 [4][128][32] (enc1's second B operand; mag is dead by then)
-    static constexpr int lol_h = mag;                            // LSTM lo rows of h  [128][32] (over e1, dead once enc2 has run)
-    static constexpr int lol_x = e3 + 128 * kSlots;              // LSTM lo rows of e3 [128][32] (over enc1's partial-sum scratch)
+    static constexpr int lol_x = e1;                             // LSTM lo rows of e3 [128][32] (over e1, dead once enc2 has run)
+    static constexpr int lol_h = e1lo;                           // LSTM lo rows of h  [128][32] (over e1lo)
     static constexpr int h = e0 + e0_floats;                     // 133632 B, atom aligned
     static constexpr int consts = h + kHid * kSlots;
     static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_bout = 1024, c_win = 1028;
@@ -133,7 +138,7 @@ struct SmemMapTC {
     static constexpr int total_floats = stage + kTcStages * stage_floats;
 };
 static_assert(SmemMapTC::e0 % 256 == 0 && SmemMapTC::h % 128 == 0 && SmemMapTC::e3 % 128 == 0 && SmemMapTC::lol_x % 128 == 0, "atom / tile alignment");
-static_assert(SmemMapTC::lol_x + 128 * kSlots <= SmemMapTC::mag + SmemMapTC::mag_floats && SmemMapTC::e0_floats >= 4 * SmemMapTC::stage_floats, "LSTM-phase borrowings");
+static_assert(SmemMapTC::e3 + 128 * kSlots <= SmemMapTC::mag + SmemMapTC::mag_floats && SmemMapTC::e0_floats >= 4 * SmemMapTC::stage_floats, "LSTM-phase borrowings");
 static_assert(SmemMapTC::e0_floats >= 2 * kSlots * SmemMapTC::zpitch, "Z planes");
 static_assert((size_t)SmemMapTC::total_floats * 4 + 256 <= 232448, "shared memory budget");
 static_assert(SmemMap::e0_floats >= 4 * 128 * kSlots, "e0 region too small");
@@ -283,6 +288,19 @@ SVAD_HD int zitem_hw(int item) { return 2 * (item & 7) + (item >> 4); }
 SVAD_HD int zitem_fr(int item) { return (item >> 3) & 1; }
 
 // Raw (unwindowed) samples of one round for this thread: xa[q] = frame 2fp, xb[q] = frame 2fp+1, m = r + 16 q.
+// Generic window fetch (context / reflect pad / zero tail resolved per sample): only the first and the last chunk of a
+// row take it, so it is kept out of line -- the fused kernel's steady-state loop has to fit the instruction cache.
+template <bool SR16, typename S>
+SVAD_COLD void stft_load_generic(int r, int fp, const S* audio, const float* ctx_in, long L, long t, float* xa, float* xb) {
+    using G = Geo<SR16>;
+#pragma unroll 1
+    for (int q = 0; q < G::NQ; q++) {
+        const int m = r + 16 * q;
+        xa[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp) + m);
+        xb[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp + 1) + m);
+    }
+}
+
 // `fast` (CTA-uniform): the whole padded window of chunk t lies inside the row, so the addresses are affine in
 // (r, q) with the reflection resolved at compile time; otherwise the generic fetch handles context / zero tail.
 template <bool SR16, typename S>
@@ -308,12 +326,10 @@ SVAD_HD void stft_load(int tid, int fp, const S* audio, const float* ctx_in, lon
             xb[q] = ld_sample(p + jb);
         }
     } else {
+        float ta[G::NQ], tb[G::NQ];   // address-taken copies: xa / xb themselves stay in registers
+        stft_load_generic<SR16, S>(r, fp, audio, ctx_in, L, t, ta, tb);
 #pragma unroll
-        for (int q = 0; q < G::NQ; q++) {
-            const int m = r + 16 * q;
-            xa[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp) + m);
-            xb[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp + 1) + m);
-        }
+        for (int q = 0; q < G::NQ; q++) { xa[q] = ta[q]; xb[q] = tb[q]; }
     }
 }
 

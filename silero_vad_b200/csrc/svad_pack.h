@@ -169,27 +169,30 @@ struct TapeTC {
     static constexpr int tile = 128 * 32;                // floats per [128 x 32] tile = one 16 KB slab
     static constexpr int e0_nslab = (Kt / 32) * 3 * 2;   // (kc, tap) x {hi, lo}: 24 / 12
     static constexpr int e1_nslab = 12;                  // (tap, kc): [64 x 32] tiles {hi | lo} = 16 KB, read by MMA warp kc
-    static constexpr int e2_nslab = 2, e3_nslab = 2;     // 32 channels x 128 floats
+    static constexpr int e2_nslab = 4;                   // (tap, channel half): [64 x 32] tiles {hi | lo}, read by MMA warp q
+    static constexpr int e3_nslab = 4;                   // (kc, hi | lo): [128 x 32] tiles, read by MMA warp 2 kc + lo
     static constexpr int l_nslab = 32;                   // (kc, gate block): one 32 KB slab = tile pair {hi | lo}, read by ONE MMA warp
     static constexpr int e0_off = 0;
     static constexpr int e1_off = e0_off + e0_nslab * tile;
     static constexpr int e2_off = e1_off + e1_nslab * tile;
-    static constexpr int e3_off = e2_off + 64 * 128;
-    static constexpr int l_off = e3_off + 64 * 128;
+    static constexpr int e3_off = e2_off + e2_nslab * tile;
+    static constexpr int l_off = e3_off + e3_nslab * tile;
     static constexpr int total = l_off + l_nslab * 2 * tile;
-    static constexpr int nsimt = e2_nslab + e3_nslab;    // slabs read by the CUDA cores
-    static constexpr int nslab = e0_nslab + e1_nslab + nsimt + l_nslab;
-    // ---- slab -> shared-memory buffer.  Buffers 0-3 are the 4 x 16 KB ring (enc0 tiles, CUDA-core slabs).  Every bulk
-    // copy costs the same ~450 cycles of fixed latency up to 32 KB (tools/ubench_ingest.cu), so the LSTM streams 32 KB
-    // tile pairs through four double-size buffers: ring halves (ids 0, 2) and the e0 region, dead once enc1 has run
-    // (ids 4, 6).  dep_delta(idx) = how many slabs back the event lies that frees the buffer(s) of slab idx.
-    static constexpr int NA = e0_nslab + e1_nslab + nsimt;   // slabs before the LSTM (a multiple of 4)
+    static constexpr int nslab = e0_nslab + e1_nslab + e2_nslab + e3_nslab + l_nslab;
+    // ---- slab -> shared-memory buffer.  Buffers 0-3 are the 4 x 16 KB ring (enc0, enc1, enc2 tiles); buffers 4-7 are the e0
+    // region, dead once enc1 has run: enc3's four slabs land there while enc2 still computes.  Every bulk copy costs the same
+    // ~450 cycles up to 32 KB (tools/ubench_ingest.cu), so the LSTM streams 32 KB tile pairs through four double-size buffers
+    // (ids 0, 2 = ring halves, 4, 6 = e0 region halves).  dep_delta(idx) = how many slabs back the event lies that frees the
+    // buffer(s) of slab idx (slabs are issued, and their consumption observed, strictly in order).
+    static constexpr int E3 = e0_nslab + e1_nslab + e2_nslab;   // first enc3 slab
+    static constexpr int NA = E3 + e3_nslab;                    // slabs before the LSTM (a multiple of 4)
     static constexpr int kBufs = 8;
-    SVAD_HD static constexpr int buf(int idx) { return idx < NA ? (idx & 3) : (((idx - NA) & 3) << 1); }
+    SVAD_HD static constexpr int buf(int idx) { return idx < E3 ? (idx & 3) : (idx < NA ? 4 + (idx - E3) : (((idx - NA) & 3) << 1)); }
     SVAD_HD static constexpr int dep_delta(int idx) {
-        if (idx < NA) return idx >= 4 ? 4 : (idx == 0 ? 4 : (idx == 3 ? 6 : 5));   // first slabs of a step wait for the last LSTM pairs
+        if (idx < E3) return idx >= 4 ? 4 : (idx == 0 ? 4 : (idx == 3 ? 6 : 5));   // first slabs of a step wait for the last LSTM pairs
+        if (idx < NA) return idx - (e0_nslab + e1_nslab - 1);                       // enc3: the last enc1 slab (reader of the e0 region)
         const int l = idx - NA;
-        return l >= 4 ? 4 : (l == 0 ? 3 : (l == 1 ? 2 : l + nsimt + 1));   // pairs 2, 3 sit in the e0 region: free once the last enc1 slab is consumed
+        return l >= 4 ? 4 : 7 - l;   // pairs 0, 1 follow enc2 slabs (0,1), (2,3) in the ring; pairs 2, 3 follow enc3 slabs (0,1), (2,3)
     }
     template <class M>
     SVAD_HD static constexpr int buf_off(int b) { return (b & 4) ? M::e0 + (b & 3) * M::stage_floats : M::stage + b * M::stage_floats; }
@@ -204,16 +207,16 @@ struct TapeTC {
         i -= e0_nslab;
         if (i < e1_nslab) return e1_off + i * tile;
         i -= e1_nslab;
-        if (i < e2_nslab) return e2_off + i * 32 * 128;
+        if (i < e2_nslab) return e2_off + i * tile;
         i -= e2_nslab;
-        if (i < e3_nslab) return e3_off + i * 32 * 128;
+        if (i < e3_nslab) return e3_off + i * tile;
         i -= e3_nslab;
         return l_off + i * 2 * tile;
     }
     SVAD_HD static constexpr int slab_len(int i) {
         if (i < e0_nslab) return tile;
         i -= e0_nslab;
-        return i < e1_nslab + nsimt ? tile : 2 * tile;   // enc1 tile pairs, enc2 / enc3 halves: 4096 floats; LSTM: a [128 x 32] tile pair
+        return i < e1_nslab + e2_nslab + e3_nslab ? tile : 2 * tile;   // enc1-3: 16 KB; LSTM: a [128 x 32] tile pair
     }
 };
 
@@ -266,7 +269,10 @@ inline bool pack_branch_tc(const TensorMap& tm, PackedBranch& out, std::string& 
         const int j = jo == 2 ? 0 : jo + 1;
         for (int kc = 0; kc < 4; kc++) pack_umma_a64(w1 + (size_t)(kc * 32) * 3 + j, 128 * 3, 3, t + T::e1_off + (jo * 4 + kc) * T::tile);
     }
-    memcpy(t + T::e2_off, v1.tape.data() + T1::e2_off, sizeof(float) * (T1::l_off - T1::e2_off));   // enc2, enc3 as in the fp32 tape
+    const float* w2 = tm.at(p + "encoder.2.reparam_conv.weight").data.data();   // [64][64][3], taps 1, 2 live
+    for (int q = 0; q < 4; q++) pack_umma_a64(w2 + (size_t)((q & 1) * 32) * 3 + (q >> 1) + 1, 64 * 3, 3, t + T::e2_off + q * T::tile);
+    const float* w3 = tm.at(p + "encoder.3.reparam_conv.weight").data.data();   // [128][64][3], tap 1 live
+    for (int kc = 0; kc < 2; kc++) pack_umma_a(w3 + (size_t)(kc * 32) * 3 + 1, 64 * 3, 3, t + T::e3_off + kc * 2 * T::tile);   // {hi | lo} = 2 slabs
     for (int kc = 0; kc < 8; kc++)
         for (int m = 0; m < 4; m++) {
             const float* src = (kc < 4 ? wih : whh) + (size_t)(m * 128) * 128 + (kc & 3) * 32;

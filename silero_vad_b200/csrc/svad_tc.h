@@ -49,61 +49,6 @@ SVAD_HD void stage_lo(int tid, const float* src, float* dst, int nrows) {
     }
 }
 
-// enc2 / enc3 in slab form (the 16 KB ring holds 32 input channels per slab); accumulators live in rg.acc
-template <int RM, class M>
-SVAD_HD void enc2_slab_tc(const Tc& tc, float* sm, const float* slab, Regs& rg, int c0, bool first, bool last) {
-    const int o = 8 * tc.warp + tc.ln;
-    if (first) {
-        const float b = sm[M::consts + M::c_b2 + o];
-#pragma unroll
-        for (int ip = 0; ip < 4; ip++) rg.acc[ip] = f2{b, b};
-    }
-#pragma unroll 4
-    for (int cc = 0; cc < 32; cc++) {
-        const int c = c0 + cc;
-        f2 x0[4], x1[4];
-        load8p(sm + M::e1 + c * kSlots, tc.lm, key_lo(c), x0);
-        load8p(sm + M::e1 + (64 + c) * kSlots, tc.lm, key_lo(c), x1);
-        const float w0 = slab[cc * 128 + o], w1 = slab[cc * 128 + 64 + o];
-#pragma unroll
-        for (int ip = 0; ip < 4; ip++) { rg.acc[ip] = ffma2_s(w0, x0[ip], rg.acc[ip]); rg.acc[ip] = ffma2_s(w1, x1[ip], rg.acc[ip]); }
-    }
-    if (last) {
-        float v[8];
-#pragma unroll
-        for (int ip = 0; ip < 4; ip++) {
-            v[2 * ip] = (2 * ip < RM) ? relu(rg.acc[ip].x) : 0.0f;
-            v[2 * ip + 1] = (2 * ip + 1 < RM) ? relu(rg.acc[ip].y) : 0.0f;
-        }
-        store8(sm + M::e2 + o * kSlots, tc.lm, key_lo(o), v);
-    }
-}
-template <int RM, class M>
-SVAD_HD void enc3_slab_tc(const Tc& tc, float* sm, const float* slab, Regs& rg, int c0, bool first, bool last) {
-    const int oc = 16 * tc.warp + 2 * tc.ln;
-    if (first) {
-        const f2 b3 = *reinterpret_cast<const f2*>(sm + M::consts + M::c_b3 + oc);
-#pragma unroll
-        for (int i = 0; i < 8; i++) rg.acc[i] = b3;
-    }
-#pragma unroll 4
-    for (int cc = 0; cc < 32; cc++) {
-        const int c = c0 + cc;
-        float x[8];
-        load8(sm + M::e2 + c * kSlots, tc.lm, key_lo(c), x);
-        const f2 w = *reinterpret_cast<const f2*>(slab + cc * 128 + oc);
-#pragma unroll
-        for (int i = 0; i < RM; i++) rg.acc[i] = ffma2_s(x[i], w, rg.acc[i]);
-    }
-    if (last) {
-        float v0[8], v1[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) { v0[i] = (i < RM) ? relu(rg.acc[i].x) : 0.0f; v1[i] = (i < RM) ? relu(rg.acc[i].y) : 0.0f; }
-        store8_tc(sm + M::e3 + oc * kSlots, tc.lm, oc, v0);
-        store8_tc(sm + M::e3 + (oc + 1) * kSlots, tc.lm, oc + 1, v1);
-    }
-}
-
 #if defined(__CUDA_ARCH__)
 #define SVAD_STAMP(k) do { if (a.dbg && first_tile == 0 && t == 2 && tc.tid == 0) a.dbg[k] = clock64(); } while (0)
 #define SVAD_CLK(v) const long long v = clock64()
@@ -123,7 +68,6 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
     const Tc tc(env.tid());
     float* sm = env.smem();
     const S* audio = static_cast<const S*>(a.audio);
-    Regs rg;
     constexpr int BT = 4 * RM;
     // epilogue coordinates: TMEM lane = weight row; warps w and w+4 share lane quarter w%4 and split the 32 slot columns
     const int lq = tc.warp & 3, row = 32 * lq + tc.lane, half = tc.warp >> 2;
@@ -358,35 +302,127 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 if (tc.lane < 16) {
                     const float b1 = sm[M::consts + M::c_b1 + o];
                     float* dst = sm + M::e1 + (tt * 64 + o) * kSlots;
+                    float* dlo = sm + M::e1lo + (tt * 64 + o) * kSlots;
 #pragma unroll
-                    for (int gq = 0; gq < 8; gq++)
-                        *reinterpret_cast<f4*>(dst + ((gq ^ key_lo(o)) << 2)) =
-                            f4{relu(v[4 * gq] + b1), relu(v[4 * gq + 1] + b1), relu(v[4 * gq + 2] + b1), relu(v[4 * gq + 3] + b1)};
+                    for (int gq = 0; gq < 8; gq++) {
+                        const f4 x = f4{relu(v[4 * gq] + b1), relu(v[4 * gq + 1] + b1), relu(v[4 * gq + 2] + b1), relu(v[4 * gq + 3] + b1)};
+                        const int pq = tc_f4(gq, o) << 2;
+                        *reinterpret_cast<f4*>(dst + pq) = x;
+                        *reinterpret_cast<f4*>(dlo + pq) = f4{lo_part(x.x), lo_part(x.y), lo_part(x.z), lo_part(x.w)};
+                    }
                 }
             }
+            env.fence_async();
             env.tc_fence_before();
             env.sync();
             SVAD_STAMP(21);
+            // ---------------- enc2: M = 64, N = 32, K = taps (1, 2) x 64 channels; tap jj reads e1 frame jj.  MMA warp q owns
+            // k-chunk q = (jj, channel half) and accumulator columns 32 q.
+            if (tc.warp < 4) {
+                env.tc_fence_after();
+                const int q = tc.warp, idx = TP::e0_nslab + TP::e1_nslab + q;
+                for (int s = 0; s < q; s++) env.slab_pass(idx - q + s);
+                const float* tile = env.slab_wait(idx);
+                SVAD_STAMP(23);
+                const auto ah = env.mma_a(tile), al = env.mma_a(tile + 64 * 32);
+                const auto bh = env.mma_b(sm + M::e1 + q * 32 * kSlots, 4096), bl = env.mma_b(sm + M::e1lo + q * 32 * kSlots, 4096);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    env.template mma<64>(32 * q, ah, bh, ks, ks != 0, 32);
+                    env.template mma<64>(32 * q, ah, bl, ks, true, 32);
+                    env.template mma<64>(32 * q, al, bh, ks, true, 32);
+                }
+                env.mma_slab_done(idx);
+                for (int s = q + 1; s < 4; s++) env.slab_pass(idx - q + s);
+                env.acc_commit();
+                SVAD_STAMP(24);
+            } else {
+                env.skip_phase(TP::phase_mask(TP::e0_nslab + TP::e1_nslab, TP::e2_nslab), TP::e2_nslab);
+                if (tc.warp == kRingWarp) {
 #pragma unroll 1
-            for (int s = 0; s < 2; s++, it++) {
-                const float* slab = env.slab_wait(TP::e0_nslab + TP::e1_nslab + s);
-                enc2_slab_tc<RM, M>(tc, sm, slab, rg, s * 32, s == 0, s == 1);
-                env.sync();
-                if (tc.warp == kRingWarp) env.ring_freed(total_slabs);
+                    for (int s = 0; s < TP::e2_nslab; s++) { env.wait_consumed_group(TP::e0_nslab + TP::e1_nslab + s, 1); env.ring_freed(total_slabs); }
+                }
             }
+            it += TP::e2_nslab;
+            env.acc_wait();
+            SVAD_STAMP(25);
+            {   // epilogue: channel 16 lq + lane (lanes 0-15), slots 16 half .. +16
+                float v[16], p[16];
+                const int o = 16 * lq + (tc.lane & 15);
+                env.tmem_ld16(lq, 16 * half, v);
+#pragma unroll
+                for (int w = 1; w < 4; w++) {
+                    env.tmem_ld16(lq, 32 * w + 16 * half, p);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] += p[i];
+                }
+                if (tc.lane < 16) {
+                    const float b2 = sm[M::consts + M::c_b2 + o];
+#pragma unroll
+                    for (int gq = 0; gq < 4; gq++) {
+                        const f4 x = f4{relu(v[4 * gq] + b2), relu(v[4 * gq + 1] + b2), relu(v[4 * gq + 2] + b2), relu(v[4 * gq + 3] + b2)};
+                        const int pq = tc_f4(4 * half + gq, o) << 2;
+                        *reinterpret_cast<f4*>(sm + M::e2 + o * kSlots + pq) = x;
+                        *reinterpret_cast<f4*>(sm + M::e2lo + o * kSlots + pq) = f4{lo_part(x.x), lo_part(x.y), lo_part(x.z), lo_part(x.w)};
+                    }
+                }
+            }
+            env.fence_async();
+            env.tc_fence_before();
+            env.sync();
             SVAD_STAMP(22);
+            // ---------------- enc3: M = 128, N = 32, K = 64 (tap 1).  MMA warp 2 kc + lo owns slab (kc, hi | lo) and columns 32 w
+            if (tc.warp < 4) {
+                env.tc_fence_after();
+                const int w = tc.warp, kc = w >> 1, idx = TP::E3 + w;
+                for (int s = 0; s < w; s++) env.slab_pass(idx - w + s);
+                const float* tile = env.slab_wait(idx);
+                SVAD_STAMP(26);
+                const auto ad = env.mma_a(tile);
+                const auto bh = env.mma_b(sm + M::e2 + kc * 32 * kSlots, 4096), bl = env.mma_b(sm + M::e2lo + kc * 32 * kSlots, 4096);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    env.mma(32 * w, ad, bh, ks, ks != 0, 32);              // w_hi * x_hi  or  w_lo * x_hi
+                    if (!(w & 1)) env.mma(32 * w, ad, bl, ks, true, 32);   // w_hi * x_lo
+                }
+                env.mma_slab_done(idx);
+                for (int s = w + 1; s < 4; s++) env.slab_pass(idx - w + s);
+                env.acc_commit();
+                SVAD_STAMP(27);
+            } else {
+                env.skip_phase(TP::phase_mask(TP::E3, TP::e3_nslab), TP::e3_nslab);
+                if (tc.warp == kRingWarp) {
 #pragma unroll 1
-            for (int s = 0; s < 2; s++, it++) {
-                const float* slab = env.slab_wait(TP::e0_nslab + TP::e1_nslab + 2 + s);
-                enc3_slab_tc<RM, M>(tc, sm, slab, rg, s * 32, s == 0, s == 1);
-                if (s == 1) stage_lo(tc.tid, sm + M::h, sm + M::lol_h, kHid);   // h is from the previous step; e1 (underneath) is dead
-                env.sync();
-                if (tc.warp == kRingWarp) env.ring_freed(total_slabs);
+                    for (int s = 0; s < TP::e3_nslab; s++) { env.wait_consumed_group(TP::E3 + s, 1); env.ring_freed(total_slabs); }
+                }
+            }
+            it += TP::e3_nslab;
+            stage_lo(tc.tid, sm + M::h, sm + M::lol_h, kHid);   // h is from the previous step; e1lo (underneath) is dead
+            SVAD_STAMP(28);
+            env.acc_wait();
+            SVAD_STAMP(29);
+            {   // epilogue: channel `row`, slots 16 half .. +16 -> e3 and its lo rows, the first half of the LSTM's B operand
+                float v[16], p[16];
+                env.tmem_ld16(lq, 16 * half, v);
+#pragma unroll
+                for (int w = 1; w < 4; w++) {
+                    env.tmem_ld16(lq, 32 * w + 16 * half, p);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] += p[i];
+                }
+                const float b3 = sm[M::consts + M::c_b3 + row];
+#pragma unroll
+                for (int gq = 0; gq < 4; gq++) {
+                    const f4 x = f4{relu(v[4 * gq] + b3), relu(v[4 * gq + 1] + b3), relu(v[4 * gq + 2] + b3), relu(v[4 * gq + 3] + b3)};
+                    const int pq = tc_f4(4 * half + gq, row) << 2;
+                    *reinterpret_cast<f4*>(sm + M::e3 + row * kSlots + pq) = x;
+                    *reinterpret_cast<f4*>(sm + M::lol_x + row * kSlots + pq) = f4{lo_part(x.x), lo_part(x.y), lo_part(x.z), lo_part(x.w)};
+                }
             }
             SVAD_STAMP(6);
             // ---------------- LSTM on the tensor core: gates[m*128 + j][slot] = sum_k W[.][k] * [e3 ; h][k][slot]
-            stage_lo(tc.tid, sm + M::e3, sm + M::lol_x, kHid);
             env.fence_async();
+            env.tc_fence_before();
             env.sync();
             SVAD_STAMP(7);
             if (tc.warp < 4) {   // MMA warp m issues gate block m

@@ -22,7 +22,7 @@ dbg.zero_()
 m.engine.forward_device(16000, B, 512 * T, 512 * T, x.data_ptr(), 0, 0, 0, 0, p.data_ptr(), T, torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 d = dbg.cpu().tolist()
-names = ["STFT", "lo-stage enc0 + sync", "enc0 MMA issue loop", "enc0 MMA tail (acc_wait)", "enc0 epilogue", "enc1 (MMA) + enc2-3 (CUDA cores)", "lo-stage LSTM + sync",
+names = ["STFT", "lo-stage enc0 + sync", "enc0 MMA issue loop", "enc0 MMA tail (acc_wait)", "enc0 epilogue", "enc1-3 (tensor core)", "lo-stage LSTM + sync",
          "LSTM MMA issue loop", "LSTM MMA tail", "LSTM epilogue + head"]
 tot = d[10] - d[0]
 for i, n in enumerate(names):
@@ -30,3 +30,4 @@ for i, n in enumerate(names):
 print(f"{'step total':28s} {tot:8d} cycles")
 print(f"enc0 loop: slab_wait {d[11]} cycles, free_upto {d[12]} cycles;  LSTM loop: slab_wait {d[13]}, free_upto {d[14]}")
 print(f"enc1 MMA phase: {d[20]-d[5]} cycles, epilogue {d[21]-d[20]};  enc2: {d[22]-d[21]};  enc3: {d[6]-d[22]}")
+print(f"enc2: slab_wait {d[23]-d[21]}, issue+commit {d[24]-d[23]}, acc_wait {d[25]-d[24]}, epilogue+sync {d[22]-d[25]};  enc3: slab_wait {d[26]-d[22]}, issue+commit {d[27]-d[26]}, stage_lo(h) {d[28]-d[27]}, acc_wait {d[29]-d[28]}, epilogue {d[6]-d[29]}")
