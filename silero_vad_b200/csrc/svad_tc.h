@@ -183,16 +183,9 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                         const auto ad = env.mma_a(tile);
                         const auto bh = env.mma_b(sm + M::mag + (f0 * M::mag_pitch + kc * 32) * kSlots, M::mag_pitch * kSlots * 4);
                         const auto bl = env.mma_b(sm + M::lo0 + (f0 * Kt + kc * 32) * kSlots, Kt * kSlots * 4);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            const bool first = (kc == 0) && (ks == 0) && (jo == 0);
-                            if (!lo) {
-                                env.mma(t0 * 32, ad, bh, ks, !first, 32 * nf);         // w_hi * x_hi
-                                env.mma(t0 * 32, ad, bl, ks, true, 32 * nf);           // w_hi * x_lo
-                            } else {
-                                env.mma(256 + t0 * 32, ad, bh, ks, !first, 32 * nf);   // w_lo * x_hi
-                            }
-                        }
+                        const bool first = (kc == 0) && (jo == 0);
+                        if (!lo) env.template mma_ks4<128, 2>(t0 * 32, ad, bh, ad, bl, ad, bl, !first, 32 * nf);   // w_hi * x_hi, w_hi * x_lo
+                        else env.template mma_ks4<128, 1>(256 + t0 * 32, ad, bh, ad, bh, ad, bh, !first, 32 * nf);   // w_lo * x_hi
                         env.mma_slab_done(s);
                     }
                 }
@@ -264,13 +257,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     const auto ah = env.mma_a(tile), al = env.mma_a(tile + 64 * 32);
                     const auto bh = env.mma_b(sm + M::e0 + (f0 * 128 + kc * 32) * kSlots, 2 * 128 * kSlots * 4);
                     const auto bl = env.mma_b(sm + M::e0lo + (f0 * 128 + kc * 32) * kSlots, 2 * 128 * kSlots * 4);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        const bool first = (jo == 0) && (ks == 0);
-                        env.template mma<64>(col, ah, bh, ks, !first, ncols);
-                        env.template mma<64>(col, ah, bl, ks, true, ncols);
-                        env.template mma<64>(col, al, bh, ks, true, ncols);
-                    }
+                    env.template mma_ks4<64, 3>(col, ah, bh, ah, bl, al, bh, jo != 0, ncols);
                     env.mma_slab_done(TP::e0_nslab + s);
                 }
                 env.acc_commit();
@@ -326,12 +313,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 SVAD_STAMP(23);
                 const auto ah = env.mma_a(tile), al = env.mma_a(tile + 64 * 32);
                 const auto bh = env.mma_b(sm + M::e1 + q * 32 * kSlots, 4096), bl = env.mma_b(sm + M::e1lo + q * 32 * kSlots, 4096);
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    env.template mma<64>(32 * q, ah, bh, ks, ks != 0, 32);
-                    env.template mma<64>(32 * q, ah, bl, ks, true, 32);
-                    env.template mma<64>(32 * q, al, bh, ks, true, 32);
-                }
+                env.template mma_ks4<64, 3>(32 * q, ah, bh, ah, bl, al, bh, false, 32);
                 env.mma_slab_done(idx);
                 for (int s = q + 1; s < 4; s++) env.slab_pass(idx - q + s);
                 env.acc_commit();
@@ -380,11 +362,8 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 SVAD_STAMP(26);
                 const auto ad = env.mma_a(tile);
                 const auto bh = env.mma_b(sm + M::e2 + kc * 32 * kSlots, 4096), bl = env.mma_b(sm + M::e2lo + kc * 32 * kSlots, 4096);
-#pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    env.mma(32 * w, ad, bh, ks, ks != 0, 32);              // w_hi * x_hi  or  w_lo * x_hi
-                    if (!(w & 1)) env.mma(32 * w, ad, bl, ks, true, 32);   // w_hi * x_lo
-                }
+                if (!(w & 1)) env.template mma_ks4<128, 2>(32 * w, ad, bh, ad, bl, ad, bl, false, 32);   // w_hi * x_hi, w_hi * x_lo
+                else env.template mma_ks4<128, 1>(32 * w, ad, bh, ad, bh, ad, bh, false, 32);            // w_lo * x_hi
                 env.mma_slab_done(idx);
                 for (int s = w + 1; s < 4; s++) env.slab_pass(idx - w + s);
                 env.acc_commit();
@@ -437,13 +416,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     const auto ah = env.mma_a(tile), al = env.mma_a(tile + TP::tile);
                     const auto bh = env.mma_b((kc < 4) ? sm + M::e3 + kc * 32 * kSlots : sm + M::h + (kc - 4) * 32 * kSlots, 4096);
                     const auto bl = env.mma_b((kc < 4) ? sm + M::lol_x + kc * 32 * kSlots : sm + M::lol_h + (kc - 4) * 32 * kSlots, 4096);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++) {
-                        const bool first = (kc == 0) && (ks == 0);
-                        env.mma(128 + m * 32, ah, bh, ks, !first, 32);   // w_hi * x_hi
-                        env.mma(128 + m * 32, ah, bl, ks, true, 32);     // w_hi * x_lo
-                        env.mma(128 + m * 32, al, bh, ks, true, 32);     // w_lo * x_hi
-                    }
+                    env.template mma_ks4<128, 3>(128 + m * 32, ah, bh, ah, bl, al, bh, kc != 0, 32);
                     env.mma_slab_done(TP::NA + s);
                 }
                 env.acc_commit();
