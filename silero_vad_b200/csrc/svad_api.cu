@@ -216,35 +216,38 @@ struct GpuEnvTC {
     // per chunk instead of per instruction: the per-instruction issue sequence (~30 SASS instructions, ~130 cycles) was
     // what bounded the MMA phases, not the tensor pipe.
 #define SVAD_MMA(A, B, P) "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], " A ", " B ", %7, " P ";\n"
+#define SVAD_MMB(A, B, P) "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], " A ", " B ", %9, " P ";\n"
 #define SVAD_KSTEP(N) "add.s64 a0, %1, " #N "*2; add.s64 b0, %2, " #N "*64; add.s64 a1, %3, " #N "*2; add.s64 b1, %4, " #N "*64; add.s64 a2, %5, " #N "*2; add.s64 b2, %6, " #N "*64;\n"
     template <int MM, int NP>
-    __device__ __forceinline__ void mma_ks4(int col, uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1, uint64_t a2, uint64_t b2, bool acc_first, int ncols) {
+    __device__ __forceinline__ void mma_ks4(int col, uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1, uint64_t a2, uint64_t b2, bool acc_first, int ncols, int ncols12 = 0) {
         const uint32_t idesc = (kIdescTf32 & ~((0x3Fu << 17) | (0x1Fu << 24))) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
+        const uint32_t idesc12 = ncols12 ? ((idesc & ~(0x3Fu << 17)) | ((uint32_t)(ncols12 >> 3) << 17)) : idesc;   // pairs 1, 2 may use another N
         const uint32_t d = tmem + (uint32_t)col, accf = acc_first ? 1u : 0u;
         if constexpr (NP == 3) {
             asm volatile("{\n.reg .pred q, p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
-                         SVAD_KSTEP(0) SVAD_MMA("a0", "b0", "p") SVAD_MMA("a1", "b1", "t") SVAD_MMA("a2", "b2", "t")
-                         SVAD_KSTEP(1) SVAD_MMA("a0", "b0", "t") SVAD_MMA("a1", "b1", "t") SVAD_MMA("a2", "b2", "t")
-                         SVAD_KSTEP(2) SVAD_MMA("a0", "b0", "t") SVAD_MMA("a1", "b1", "t") SVAD_MMA("a2", "b2", "t")
-                         SVAD_KSTEP(3) SVAD_MMA("a0", "b0", "t") SVAD_MMA("a1", "b1", "t") SVAD_MMA("a2", "b2", "t") "}\n"
-                         ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(idesc), "r"(accf) : "memory");
+                         SVAD_KSTEP(0) SVAD_MMA("a0", "b0", "p") SVAD_MMB("a1", "b1", "t") SVAD_MMB("a2", "b2", "t")
+                         SVAD_KSTEP(1) SVAD_MMA("a0", "b0", "t") SVAD_MMB("a1", "b1", "t") SVAD_MMB("a2", "b2", "t")
+                         SVAD_KSTEP(2) SVAD_MMA("a0", "b0", "t") SVAD_MMB("a1", "b1", "t") SVAD_MMB("a2", "b2", "t")
+                         SVAD_KSTEP(3) SVAD_MMA("a0", "b0", "t") SVAD_MMB("a1", "b1", "t") SVAD_MMB("a2", "b2", "t") "}\n"
+                         ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(idesc), "r"(accf), "r"(idesc12) : "memory");
         } else if constexpr (NP == 2) {
             asm volatile("{\n.reg .pred q, p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
-                         SVAD_KSTEP(0) SVAD_MMA("a0", "b0", "p") SVAD_MMA("a1", "b1", "t")
-                         SVAD_KSTEP(1) SVAD_MMA("a0", "b0", "t") SVAD_MMA("a1", "b1", "t")
-                         SVAD_KSTEP(2) SVAD_MMA("a0", "b0", "t") SVAD_MMA("a1", "b1", "t")
-                         SVAD_KSTEP(3) SVAD_MMA("a0", "b0", "t") SVAD_MMA("a1", "b1", "t") "}\n"
-                         ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(idesc), "r"(accf) : "memory");
+                         SVAD_KSTEP(0) SVAD_MMA("a0", "b0", "p") SVAD_MMB("a1", "b1", "t")
+                         SVAD_KSTEP(1) SVAD_MMA("a0", "b0", "t") SVAD_MMB("a1", "b1", "t")
+                         SVAD_KSTEP(2) SVAD_MMA("a0", "b0", "t") SVAD_MMB("a1", "b1", "t")
+                         SVAD_KSTEP(3) SVAD_MMA("a0", "b0", "t") SVAD_MMB("a1", "b1", "t") "}\n"
+                         ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(idesc), "r"(accf), "r"(idesc12) : "memory");
         } else {
             asm volatile("{\n.reg .pred q, p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
                          SVAD_KSTEP(0) SVAD_MMA("a0", "b0", "p")
                          SVAD_KSTEP(1) SVAD_MMA("a0", "b0", "t")
                          SVAD_KSTEP(2) SVAD_MMA("a0", "b0", "t")
                          SVAD_KSTEP(3) SVAD_MMA("a0", "b0", "t") "}\n"
-                         ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(idesc), "r"(accf) : "memory");
+                         ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(idesc), "r"(accf), "r"(idesc12) : "memory");
         }
     }
 #undef SVAD_MMA
+#undef SVAD_MMB
 #undef SVAD_KSTEP
     __device__ __forceinline__ void mma_slab_done(int it) {
         if (elect())

@@ -108,14 +108,15 @@ struct SmemMap {
 struct SmemMapTC {
     static constexpr bool kTC = true;
     static constexpr int mag_pitch = 132;                        // rows per frame
-    static constexpr int mag = 0;
+    static constexpr int h = 0;                                  // LSTM hidden state [128][32]; below its lo rows (descriptor strides are unsigned)
+    static constexpr int mag = h + kHid * kSlots;
     static constexpr int mag_floats = 4 * mag_pitch * kSlots;    // 16896 floats = 132 x 512 B
     // activations after enc0 (all as tcgen05 B rows; hi = the fp32 value, lo = its tf32 truncation error), over the dead mag rows
     static constexpr int e1 = mag;                               // [2][64][32]
     static constexpr int e1lo = e1 + 2 * 64 * kSlots;
     static constexpr int e2 = e1lo + 2 * 64 * kSlots;            // [64][32]
     static constexpr int e2lo = e2 + 64 * kSlots;
-    static constexpr int e3 = e2lo + 64 * kSlots;                // [128][32]
+    static constexpr int e3 = e1;                                // [128][32] (over e1, dead once enc2 has run)
     static constexpr int e0 = mag + mag_floats;
     static constexpr int zpitch = 257;
     static constexpr int e0_floats = 129 * 128;                  // 66048 B >= Z planes (2*32*257) and e0 (4*128*32)
@@ -123,10 +124,9 @@ struct SmemMapTC {
     static constexpr int zim = e0 + kSlots * zpitch;
     static constexpr int lo0 = e0;                               // enc0 lo tiles [4][Kt][32] (after the STFT, before e0 is written)
     static constexpr int e0lo = mag;                             // lo parts of e0 [4][128][32] (enc1's second B operand; mag is dead by then)
-    static constexpr int lol_x = e1;                             // LSTM lo rows of e3 [128][32] (over e1, dead once enc2 has run)
-    static constexpr int lol_h = e1lo;                           // LSTM lo rows of h  [128][32] (over e1lo)
-    static constexpr int h = e0 + e0_floats;                     // 133632 B, atom aligned
-    static constexpr int consts = h + kHid * kSlots;
+    static constexpr int lol_x = e1lo;                           // LSTM lo rows of e3 [128][32] (over e1lo), one N atom above e3
+    static constexpr int lol_h = e2lo + 64 * kSlots;             // LSTM lo rows of h  [128][32]
+    static constexpr int consts = e0 + e0_floats;
     static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_bout = 1024, c_win = 1028;
     static constexpr int c_twr = c_win + 256, c_twi = c_twr + 256;
     static constexpr int c_wnyq = c_twi + 256;                   // enc0 weights of the Nyquist bin: [3 taps][128]
@@ -138,7 +138,7 @@ struct SmemMapTC {
     static constexpr int total_floats = stage + kTcStages * stage_floats;
 };
 static_assert(SmemMapTC::e0 % 256 == 0 && SmemMapTC::h % 128 == 0 && SmemMapTC::e3 % 128 == 0 && SmemMapTC::lol_x % 128 == 0, "atom / tile alignment");
-static_assert(SmemMapTC::e3 + 128 * kSlots <= SmemMapTC::mag + SmemMapTC::mag_floats && SmemMapTC::e0_floats >= 4 * SmemMapTC::stage_floats, "LSTM-phase borrowings");
+static_assert(SmemMapTC::lol_h + 128 * kSlots <= SmemMapTC::mag + SmemMapTC::mag_floats && SmemMapTC::lol_x > SmemMapTC::e3 && SmemMapTC::lol_h > SmemMapTC::h && SmemMapTC::e0_floats >= 4 * SmemMapTC::stage_floats, "LSTM-phase borrowings");
 static_assert(SmemMapTC::e0_floats >= 2 * kSlots * SmemMapTC::zpitch, "Z planes");
 static_assert((size_t)SmemMapTC::total_floats * 4 + 256 <= 232448, "shared memory budget");
 static_assert(SmemMap::e0_floats >= 4 * 128 * kSlots, "e0 region too small");
@@ -419,6 +419,31 @@ SVAD_HD void store8_tc(float* row, int lm, int ch, const float (&x)[8]) {
 }
 SVAD_HD float relu(float v) { return v > 0.0f ? v : 0.0f; }   // NaN -> 0 like fmaxf(v, 0)
 SVAD_HD float sigmoid_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+// Gate math of the tensor-core kernel: one MUFU.EX2 + one MUFU.RCP (+ one Newton step) per activation instead of libm expf /
+// tanhf / IEEE division (~35 instead of ~115 instructions per LSTM cell).  Absolute error ~1e-7 per activation (ex2.approx: 2 ulp
+// of e^x, which enters scaled by <= 1/4 resp. 1/2), saturating correctly for large |v| (e^x = inf -> 0 / 1).
+SVAD_HD float rcp_newton(float y) {   // 1 / y for y in [1, inf]
+#if defined(__CUDA_ARCH__)
+    const float r = __fdividef(1.0f, y);
+    return (y < 1e30f) ? fmaf(r, fmaf(-y, r, 1.0f), r) : r;   // no refinement near overflow (y * r would be inf * 0)
+#else
+    return 1.0f / y;
+#endif
+}
+SVAD_HD float sigmoid_fast(float v) {
+#if defined(__CUDA_ARCH__)
+    return rcp_newton(1.0f + __expf(-v));
+#else
+    return 1.0f / (1.0f + expf(-v));
+#endif
+}
+SVAD_HD float tanh_fast(float v) {
+#if defined(__CUDA_ARCH__)
+    return fmaf(-2.0f, rcp_newton(1.0f + __expf(2.0f * v)), 1.0f);
+#else
+    return tanhf(v);
+#endif
+}
 
 // ---------------------------------------------------------------- enc0
 // acc[t][i] = (col u=0, col u=1) for t<4 frames, i<8 rows -> rg.acc[t*8+i]; cols 16*warp + 2*ln + u.

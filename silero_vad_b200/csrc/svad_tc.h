@@ -413,10 +413,12 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     SVAD_CLK(c0);
                     const float* tile = env.slab_wait(TP::NA + s);
                     SVAD_CLK(c1); SVAD_ACC(13, c1 - c0);
+                    // one instruction covers w_hi * [x_hi | x_lo]: the lo rows sit one N atom (LBO) above the hi rows and land in
+                    // the block's second 32 columns; w_lo * x_hi (N = 32) accumulates into the first 32
                     const auto ah = env.mma_a(tile), al = env.mma_a(tile + TP::tile);
-                    const auto bh = env.mma_b((kc < 4) ? sm + M::e3 + kc * 32 * kSlots : sm + M::h + (kc - 4) * 32 * kSlots, 4096);
-                    const auto bl = env.mma_b((kc < 4) ? sm + M::lol_x + kc * 32 * kSlots : sm + M::lol_h + (kc - 4) * 32 * kSlots, 4096);
-                    env.template mma_ks4<128, 3>(128 + m * 32, ah, bh, ah, bl, al, bh, kc != 0, 32);
+                    const float* xh = (kc < 4) ? sm + M::e3 + kc * 32 * kSlots : sm + M::h + (kc - 4) * 32 * kSlots;
+                    const auto bhl = env.mma_b(xh, ((kc < 4) ? (M::lol_x - M::e3) : (M::lol_h - M::h)) * 4);
+                    env.template mma_ks4<128, 2>(128 + m * 64, ah, bhl, al, bhl, al, bhl, kc != 0, 64, 32);
                     env.mma_slab_done(TP::NA + s);
                 }
                 env.acc_commit();
@@ -434,19 +436,30 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
             // epilogue: hidden unit `row`, slots 16*half..+16
             {
                 float gi[16], gf[16], gg[16], go[16];
-                env.tmem_ld16(lq, 128 + 0 * 32 + 16 * half, gi);
-                env.tmem_ld16(lq, 128 + 1 * 32 + 16 * half, gf);
-                env.tmem_ld16(lq, 128 + 2 * 32 + 16 * half, gg);
-                env.tmem_ld16(lq, 128 + 3 * 32 + 16 * half, go);
+                {
+                    float p[16];
+                    env.tmem_ld16(lq, 128 + 0 * 64 + 16 * half, gi); env.tmem_ld16(lq, 128 + 0 * 64 + 32 + 16 * half, p);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) gi[i] += p[i];
+                    env.tmem_ld16(lq, 128 + 1 * 64 + 16 * half, gf); env.tmem_ld16(lq, 128 + 1 * 64 + 32 + 16 * half, p);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) gf[i] += p[i];
+                    env.tmem_ld16(lq, 128 + 2 * 64 + 16 * half, gg); env.tmem_ld16(lq, 128 + 2 * 64 + 32 + 16 * half, p);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) gg[i] += p[i];
+                    env.tmem_ld16(lq, 128 + 3 * 64 + 16 * half, go); env.tmem_ld16(lq, 128 + 3 * 64 + 32 + 16 * half, p);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) go[i] += p[i];
+                }
                 const float* bl = sm + M::consts + M::c_bl;
                 const float bi = bl[row], bf = bl[128 + row], bg = bl[256 + row], bo = bl[384 + row];
                 float hv[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const float ig = sigmoid_acc(gi[i] + bi), fg = sigmoid_acc(gf[i] + bf), g2 = tanhf(gg[i] + bg), og = sigmoid_acc(go[i] + bo);
+                    const float ig = sigmoid_fast(gi[i] + bi), fg = sigmoid_fast(gf[i] + bf), g2 = tanh_fast(gg[i] + bg), og = sigmoid_fast(go[i] + bo);
                     const float cn = fmaf(fg, cst[i], ig * g2);
                     cst[i] = cn;
-                    hv[i] = og * tanhf(cn);
+                    hv[i] = og * tanh_fast(cn);
                 }
                 float* hrow = sm + M::h + row * kSlots;
 #pragma unroll

@@ -152,11 +152,12 @@ struct EmuEnvTC {
         }
     }
     template <int MM, int NP>
-    void mma_ks4(int col, const float* a0, BDesc b0, const float* a1, BDesc b1, const float* a2, BDesc b2, bool acc_first, int ncols) {
+    void mma_ks4(int col, const float* a0, BDesc b0, const float* a1, BDesc b1, const float* a2, BDesc b2, bool acc_first, int ncols, int ncols12 = 0) {
+        if (!ncols12) ncols12 = ncols;
         for (int ks = 0; ks < 4; ks++) {
             mma<MM>(col, a0, b0, ks, ks != 0 || acc_first, ncols);
-            if (NP >= 2) mma<MM>(col, a1, b1, ks, true, ncols);
-            if (NP >= 3) mma<MM>(col, a2, b2, ks, true, ncols);
+            if (NP >= 2) mma<MM>(col, a1, b1, ks, true, ncols12);
+            if (NP >= 3) mma<MM>(col, a2, b2, ks, true, ncols12);
         }
     }
     void mma_slab_done(int) { if (lane0()) sh->released[seen - 1].fetch_add(1, std::memory_order_acq_rel); }
