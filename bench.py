@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--chunks", type=int, default=64, help="chunks per stream per step")
     ap.add_argument("--sr", type=int, default=16000, choices=[16000, 8000])
-    ap.add_argument("--kernel", default="tc", choices=["tc", "fp32"], help="tc: tcgen05 split-TF32 for enc0 + LSTM (default); fp32: all CUDA cores")
+    ap.add_argument("--kernel", default="tc", choices=["tc", "fp32"], help="tc: tcgen05 split-TF32 for every dense layer (default); fp32: all CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -270,7 +270,7 @@ def run_b200(args):
                    "sr": sr, "batch_per_gpu": B, "chunks_per_stream": T, "global_streams": B * world,
                    "l2": "inputs (%.0f MB/step/GPU) larger than L2, no flush needed" % (B * L * 4 / 1e6),
                    "parallelism": f"dp{world}: streams sharded, weights replicated, NCCL all-gather of probabilities" if world > 1 else "single GPU",
-                   "kernel": ("svad_fused_tc (tcgen05 split-TF32 for enc0 + LSTM, fp32 CUDA cores elsewhere)" if args.kernel == "tc" else "svad_fused_fp32 (fp32 FFMA2, CUDA cores only)")},
+                   "kernel": ("svad_fused_tc (tcgen05 split-TF32 for enc0-3 + LSTM; STFT, gate math and head on the CUDA cores)" if args.kernel == "tc" else "svad_fused_fp32 (fp32 FFMA2, CUDA cores only)")},
         "gpu_launches": int(launches),
         "kernel_ms": kernel_ms,
         "clocks": clocks,

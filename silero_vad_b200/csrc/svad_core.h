@@ -293,7 +293,7 @@ SVAD_HD int zitem_fr(int item) { return (item >> 3) & 1; }
 template <bool SR16, typename S>
 SVAD_COLD void stft_load_generic(int r, int fp, const S* audio, const float* ctx_in, long L, long t, float* xa, float* xb) {
     using G = Geo<SR16>;
-#pragma unroll 1
+#pragma unroll 4
     for (int q = 0; q < G::NQ; q++) {
         const int m = r + 16 * q;
         xa[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp) + m);

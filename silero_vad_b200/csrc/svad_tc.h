@@ -49,6 +49,13 @@ SVAD_HD void stage_lo(int tid, const float* src, float* dst, int nrows) {
     }
 }
 
+#if defined(SVAD_EXACT_GATES)
+#define SVAD_SIG sigmoid_acc
+#define SVAD_TANH tanhf
+#else
+#define SVAD_SIG sigmoid_fast
+#define SVAD_TANH tanh_fast
+#endif
 #if defined(__CUDA_ARCH__)
 #define SVAD_STAMP(k) do { if (a.dbg && first_tile == 0 && t == 2 && tc.tid == 0) a.dbg[k] = clock64(); } while (0)
 #define SVAD_CLK(v) const long long v = clock64()
@@ -456,10 +463,10 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 float hv[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const float ig = sigmoid_fast(gi[i] + bi), fg = sigmoid_fast(gf[i] + bf), g2 = tanh_fast(gg[i] + bg), og = sigmoid_fast(go[i] + bo);
+                    const float ig = SVAD_SIG(gi[i] + bi), fg = SVAD_SIG(gf[i] + bf), g2 = SVAD_TANH(gg[i] + bg), og = SVAD_SIG(go[i] + bo);
                     const float cn = fmaf(fg, cst[i], ig * g2);
                     cst[i] = cn;
-                    hv[i] = og * tanh_fast(cn);
+                    hv[i] = og * SVAD_TANH(cn);
                 }
                 float* hrow = sm + M::h + row * kSlots;
 #pragma unroll
