@@ -45,9 +45,9 @@ void svad_engine_destroy(svad_engine* e);
 
 /* Streams per CTA tile = 4*rows; rows in [4,8], 0 = choose per call (default). Testing / tuning knob. */
 int svad_engine_set_tile_rows(svad_engine* e, int rows);
-/* Kernel selection: 1 = tensor-core kernel (default: tcgen05, split-precision TF32 for enc0 and the LSTM cell,
- * everything else fp32 on the CUDA cores), 0 = all-fp32 CUDA-core kernel.  Both meet the parity bar; their
- * probabilities differ by ~5e-6. */
+/* Kernel selection: 1 = tensor-core kernel (default: tcgen05, split-precision TF32 for the four encoder convolutions
+ * and the LSTM cell; STFT, gate math and head fp32 on the CUDA cores), 0 = all-fp32 CUDA-core kernel.  Both meet the
+ * parity bar; their probabilities differ by ~5e-6, the carried cell state by ~5e-6 relative. */
 int svad_engine_set_kernel(svad_engine* e, int kernel);
 /* Batches of up to `streams` streams run on the small-batch cluster kernel (8-CTA clusters with the network split
  * across their shared memories; the latency path).  Default 256 (measured crossover with the tile kernels); 0 disables it. */

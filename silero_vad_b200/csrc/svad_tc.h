@@ -1,18 +1,21 @@
-// svad_tc.h -- tensor-core variant of the fused kernel: enc0 (47 % of the MACs) and the LSTM cell (37 %) run on
-// tcgen05 (5th-gen tensor cores, accumulators in TMEM); the STFT, enc1-3, gate math and head stay on the CUDA cores.
+// svad_tc.h -- tensor-core variant of the fused kernel: the four encoder convolutions and the LSTM cell (all dense-layer
+// MACs) run on tcgen05 (5th-gen tensor cores, accumulators in TMEM); the STFT, the epilogues (bias, ReLU, lo split, gate
+// math) and the head stay on the CUDA cores.
 //
-// Orientation: the WEIGHTS are the M = 128 operand (A, K-major SWIZZLE_128B tiles streamed from the tape), the
-// stream slots are N = 32 (B, MN-major SWIZZLE_128B_BASE32B = the activation rows as they already sit in shared
-// memory), K = 8 per instruction, fp32 accumulate.  tcgen05 cost is proportional to N, so a 28-32 stream tile per
-// CTA keeps the tensor pipe efficient while the activations of a tile still fit one SM.
+// Orientation: the WEIGHTS are the M operand (A, K-major SWIZZLE_128B tiles streamed from the tape: 128 rows for enc0 /
+// enc3 / a gate block, 64 rows for enc1 / enc2), the stream slots are N (B, MN-major SWIZZLE_128B_BASE32B = the activation
+// rows as they already sit in shared memory; several 32-slot atoms -- frames, or hi | lo rows -- at the descriptor's LBO
+// stride), K = 8 per instruction, fp32 accumulate.  One tcgen05.mma costs 41 / 49 / 65 cycles of the tensor pipe at
+// N = 32 / 64 / 128 (tools/ubench_umma.cu), so instructions are made as wide in N as the layer allows.
 //
 // Precision: plain TF32 fails parity (2e-3).  Split precision x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // with hi = the fp32 container as is (the tensor core truncates it to tf32; measured in tools/umma_unit.cu) and
-// lo = v - trunc_tf32(v), exact in fp32: three MMAs per k-step, products carry ~21 mantissa bits.
-// The activation buffer itself is the "hi" operand; only the "lo" rows are staged (one pass of the CUDA cores).
+// lo = v - trunc_tf32(v), exact in fp32; products carry ~21 mantissa bits.  The activation buffer itself is the "hi"
+// operand; the producing epilogue writes the "lo" rows next to it (mag and h are split by one CUDA-core pass).
 //
 // Env (GPU: svad_api.cu, CPU emulator: tests/emu) adds to the fp32 kernel's interface:
-//   mma(col, a_tile, ks, b_rows, acc)   D[128 x 32 @ TMEM column col] (+)= A_tile[:, ks*8..+8] * B_rows[8 x 32]
+//   mma_ks4<M, NP>(col, a0, b0, a1, b1, a2, b2, acc, n, n12)   the 4 k-steps of one 32-wide k-chunk, per k-step NP descriptor
+//                                       pairs (A_i, B_i) into D[M x n @ TMEM column col], issued from ONE elected region
 //   mma_slab_done(it) / acc_commit()    tcgen05.commit to the stage's / the layer's mbarrier      (issuer thread)
 //   acc_wait()                          all threads: the layer's accumulators are complete
 //   tmem_ld16(lane_quarter, col, v)     16 consecutive columns of this thread's TMEM lane
@@ -25,7 +28,7 @@
 //     wait_consumed_group(idx, 1)  the MMAs reading slab idx have completed (each slab has ONE consuming MMA warp, and the
 //                                  warps drift apart, so every slab is waited for individually, in order)
 //     ring_freed(total)   the next slab (in order) is consumed: advance and issue every slab whose buffer is now free
-//   MMA warps: mma_a(tile) / mma_b(rows, lbo) descriptors; mma(col, adesc, bdesc, ks, acc, ncols) issues one instruction
+//   MMA warps: mma_a(tile) / mma_b(rows, lbo) descriptors; mma<M>(col, adesc, bdesc, ks, acc, ncols) issues one instruction
 #pragma once
 #include "svad_tile.h"
 

@@ -14,6 +14,9 @@ namespace cg = cooperative_groups;
 #ifndef KSTAGES
 #define KSTAGES 4
 #endif
+#ifndef KISSUERS
+#define KISSUERS 1   // bulk copies are issued round-robin by this many different warps
+#endif
 constexpr int kStage = KSTAGE, kStages = KSTAGES;
 
 __device__ __forceinline__ uint32_t su32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(128, 1) ingest(const char* tape, int tape_byte
     long long t0 = clock64();
     // issue-ahead by kStages-1; consumers just touch one word per slab (we measure the copy engine, not LDS)
     for (long it = 0; it < total + kStages - 1; it++) {
-        if (it < total && threadIdx.x == 0) {
+        if (it < total && threadIdx.x == 32 * (int)(it % KISSUERS)) {
             const int stage = it % kStages;
             const uint32_t bar = su32(full + stage);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStage) : "memory");
@@ -95,7 +98,9 @@ int main() {
     const int bytes = 1792 * 1024;   // ~ hi+lo weight tape of the 16 kHz branch
     char* tape; cudaMalloc(&tape, bytes); cudaMemset(tape, 0, bytes);
     printf("%s, %d SMs, tape %d KB\n", p.name, p.multiProcessorCount, bytes / 1024);
-    printf("stage %d B x %d stages\n", kStage, kStages);
+    printf("stage %d B x %d stages, %d issuing warps\n", kStage, kStages, KISSUERS);
     run<1>(tape, bytes, p.multiProcessorCount);
+    run<2>(tape, bytes, p.multiProcessorCount);   // every CTA of the cluster fetches 1/C of each stage and multicasts it
+    run<4>(tape, bytes, p.multiProcessorCount);
     return 0;
 }
