@@ -60,9 +60,9 @@ SVAD_HD void stage_lo(int tid, const float* src, float* dst, int nrows) {
 #define SVAD_TANH tanh_fast
 #endif
 #if defined(__CUDA_ARCH__)
-#define SVAD_STAMP(k) do { if (a.dbg && first_tile == 0 && t == 2 && tc.tid == 0) a.dbg[k] = clock64(); } while (0)
+#define SVAD_STAMP(k) do { if (a.dbg && first_tile == 0 && t == a.T / 2 && tc.tid == 0) a.dbg[k] = clock64(); } while (0)
 #define SVAD_CLK(v) const long long v = clock64()
-#define SVAD_ACC(k, d) do { if (a.dbg && first_tile == 0 && t == 2 && tc.tid == 0) a.dbg[k] += (d); } while (0)
+#define SVAD_ACC(k, d) do { if (a.dbg && first_tile == 0 && t == a.T / 2 && tc.tid == 0) a.dbg[k] += (d); } while (0)
 #else
 #define SVAD_STAMP(k) do { } while (0)
 #define SVAD_CLK(v) do { } while (0)

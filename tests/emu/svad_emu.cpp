@@ -242,3 +242,46 @@ extern "C" int svad_emu_forward(const char* weights, int sr, int rm, int B, long
     }
     return 0;
 }
+
+// ---- static checks of the tensor-core weight stream tables (TapeTC): tape tiling, buffer bounds, and that no slab is ever
+// copied into shared memory that an earlier, possibly unconsumed slab still occupies
+template <bool SR16>
+static int tape_check(char* msg, int n) {
+    using TP = TapeTC<SR16>;
+    using M = SmemMapTC;
+    auto fail = [&](const char* what, int a, int b) { snprintf(msg, n, "%s (%d, %d)", what, a, b); return 1; };
+    int off = 0;
+    for (int i = 0; i < TP::nslab; i++) {
+        if (TP::slab_off(i) != off) return fail("tape is not tiled by the slabs at slab", i, TP::slab_off(i));
+        off += TP::slab_len(i);
+        const int b = TP::buf(i), lo = TP::template buf_off<M>(b), hi = lo + TP::slab_len(i);
+        if (b < 0 || b >= TP::kBufs) return fail("buffer id out of range", i, b);
+        const bool ring = b < 4;
+        const int r0 = ring ? M::stage : M::e0, r1 = ring ? M::stage + kTcStages * M::stage_floats : M::e0 + M::e0_floats;
+        if (lo < r0 || hi > r1) return fail("slab leaves its buffer region", i, b);
+        if ((lo * 4) % 1024) return fail("tile base not 1 KB aligned", i, lo * 4);
+        // the e0 region holds Z planes / lo0 / e0 until the last enc1 slab has been consumed
+        if (!ring && i - TP::dep_delta(i) < TP::e0_nslab + TP::e1_nslab - 1) return fail("e0-region buffer filled before enc1 is done", i, TP::dep_delta(i));
+    }
+    if (off != TP::total) return fail("tape length", off, TP::total);
+    if (TP::NA % 4 || TP::l_nslab % 4) return fail("phase lengths must be multiples of the ring depth", TP::NA, TP::l_nslab);
+    for (int g = TP::nslab; g < 3 * TP::nslab; g++) {   // steady state: steps 1 and 2 of 3
+        const int i = g % TP::nslab, d = TP::dep_delta(i);
+        if (d < 1) return fail("dep_delta < 1", i, d);
+        const int lo = TP::template buf_off<M>(TP::buf(i)), hi = lo + TP::slab_len(i);
+        for (int gp = g - d + 1; gp < g; gp++) {   // issued earlier, not known to be consumed when slab g goes out
+            const int j = gp % TP::nslab, lj = TP::template buf_off<M>(TP::buf(j)), hj = lj + TP::slab_len(j);
+            if (lo < hj && lj < hi) return fail("slab overwrites an unconsumed slab", i, j);
+        }
+        // and the copy must not wait for a slab that comes AFTER something it blocks: d <= slabs in flight capacity
+        if (d > TP::nslab) return fail("dep_delta larger than a step", i, d);
+    }
+    for (int first = 0; first < TP::nslab; first += 4) {
+        uint32_t m = 0;
+        for (int k = 0; k < 4; k++) m ^= 1u << TP::buf(first + k);
+        if (m != TP::phase_mask(first, 4)) return fail("phase_mask", first, (int)m);
+    }
+    snprintf(msg, n, "ok: %d slabs, %d floats", TP::nslab, TP::total);
+    return 0;
+}
+extern "C" int svad_emu_tape_check(int sr, char* msg, int n) { return sr == 16000 ? tape_check<true>(msg, n) : tape_check<false>(msg, n); }

@@ -128,6 +128,16 @@ def test_emulated_kernel_matches_oracle(emu, oracle, fixtures, sr, rm, B):
     assert np.array_equal(cx_e, cx_o)
 
 
+@pytest.mark.parametrize("sr", [16000, 8000])
+def test_tensor_core_weight_stream_tables(emu, sr):
+    """TapeTC (svad_pack.h): the slabs tile the tape, every buffer lies in its region and is 1 KB aligned, the e0-region buffers
+    are not refilled before enc1 (their last reader) is done, and no copy can land on a slab that may still be unconsumed
+    when it is issued (dep_delta vs the buffer map, simulated over three steps)."""
+    msg = ctypes.create_string_buffer(256)
+    rc = emu.svad_emu_tape_check(sr, msg, 256)
+    assert rc == 0, msg.value.decode()
+
+
 @pytest.mark.parametrize("sr,rm,B", [(16000, 8, 5), (16000, 7, 37), (8000, 8, 5)])
 def test_emulated_tensor_core_kernel_matches_oracle(emu, oracle, fixtures, sr, rm, B):
     """The tensor-core schedule (svad_tc.h) on CPU threads: tcgen05.mma modelled as truncated-TF32 products read through

@@ -1,4 +1,4 @@
-"""Per-phase clock64 stamps of one step of the tensor-core kernel (CTA 0): python tools/tc_phase_times.py [B] [T] [rows]"""
+"""Per-phase clock64 stamps of the middle step (t = T/2) of the tensor-core kernel (CTA 0, thread 0): python tools/tc_phase_times.py [B] [T] [rows]"""
 import ctypes, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -28,6 +28,6 @@ tot = d[10] - d[0]
 for i, n in enumerate(names):
     print(f"{n:28s} {d[i+1]-d[i]:8d} cycles  {100*(d[i+1]-d[i])/tot:5.1f}%")
 print(f"{'step total':28s} {tot:8d} cycles")
-print(f"enc0 loop: slab_wait {d[11]} cycles, free_upto {d[12]} cycles;  LSTM loop: slab_wait {d[13]}, free_upto {d[14]}")
+print(f"waiting for weights (warp 0): enc0 loop {d[11]} cycles, LSTM loop {d[13]} cycles")
 print(f"enc1 MMA phase: {d[20]-d[5]} cycles, epilogue {d[21]-d[20]};  enc2: {d[22]-d[21]};  enc3: {d[6]-d[22]}")
 print(f"enc2: slab_wait {d[23]-d[21]}, issue+commit {d[24]-d[23]}, acc_wait {d[25]-d[24]}, epilogue+sync {d[22]-d[25]};  enc3: slab_wait {d[26]-d[22]}, issue+commit {d[27]-d[26]}, stage_lo(h) {d[28]-d[27]}, acc_wait {d[29]-d[28]}, epilogue {d[6]-d[29]}")
