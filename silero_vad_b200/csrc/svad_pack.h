@@ -168,6 +168,8 @@ struct TapeTC {
     static constexpr int Kt = G::F - 1;                  // 128 / 64 bins on the tensor core
     static constexpr int tile = 128 * 32;                // floats per [128 x 32] tile = one 16 KB slab
     static constexpr int e0_nslab = (Kt / 32) * 3 * 2;   // (kc, tap) x {hi, lo}: 24 / 12
+    SVAD_HD static constexpr int e0_pair_kc(int pr) { return pr < Kt / 32 ? pr : (pr - Kt / 32) >> 1; }
+    SVAD_HD static constexpr int e0_pair_tap(int pr) { return pr < Kt / 32 ? 1 : (((pr - Kt / 32) & 1) ? 2 : 0); }
     static constexpr int e1_nslab = 12;                  // (tap, kc): [64 x 32] tiles {hi | lo} = 16 KB, read by MMA warp kc
     static constexpr int e2_nslab = 4;                   // (tap, channel half): [64 x 32] tiles {hi | lo}, read by MMA warp q
     static constexpr int e3_nslab = 4;                   // (kc, hi | lo): [128 x 32] tiles, read by MMA warp 2 kc + lo
@@ -259,11 +261,12 @@ inline bool pack_branch_tc(const TensorMap& tm, PackedBranch& out, std::string& 
     const float* bhh = tm.at(p + "decoder.rnn.bias_hh").data.data();
     out.tape.assign(T::total, 0.0f);
     float* t = out.tape.data();
-    for (int kc = 0; kc < T::Kt / 32; kc++)
-        for (int jo = 0; jo < 3; jo++) {   // tap order 1, 0, 2 (see svad_tc.h)
-            const int j = jo == 0 ? 1 : (jo == 1 ? 0 : 2);
-            pack_umma_a(w0 + (size_t)(kc * 32) * 3 + j, (long)G::F * 3, 3, t + T::e0_off + (kc * 3 + jo) * 2 * T::tile);   // {hi | lo} = 2 slabs
-        }
+    // enc0 tile pairs {hi | lo} in issue order: first tap 1 of every k-chunk (the only tap that reaches all four frames, so the
+    // first instruction into each of the four accumulators overwrites every column), then taps 0 and 2 chunk by chunk
+    for (int pr = 0; pr < T::e0_nslab / 2; pr++) {
+        const int kc = T::e0_pair_kc(pr), j = T::e0_pair_tap(pr);
+        pack_umma_a(w0 + (size_t)(kc * 32) * 3 + j, (long)G::F * 3, 3, t + T::e0_off + pr * 2 * T::tile);   // {hi | lo} = 2 slabs
+    }
     const float* w1 = tm.at(p + "encoder.1.reparam_conv.weight").data.data();   // [64][128][3]
     for (int jo = 0; jo < 3; jo++) {   // tap order 1, 2, 0: the first slab of every MMA warp covers both output frames
         const int j = jo == 2 ? 0 : jo + 1;

@@ -171,31 +171,31 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
             env.tc_fence_before();     // the previous step's tcgen05.ld of these TMEM columns are done
             env.sync();
             SVAD_STAMP(2);
-            // Warps 0-3 are the MMA warps (each walks every slab: wait for it to land, use it or just release it, so the
-            // "stage consumed" barriers always collect 4 arrivals).  enc0: warp 0 issues; one instruction covers all frames a
-            // tap contributes to (N = 96 or 128: the frames are consecutive 32-column atoms of the B operand, LBO = frame pitch).
-            // Tap order in the tape is 1, 0, 2 so that the very first MMA (tap 1) overwrites all four frame blocks.
+            // enc0: one instruction covers all frames a tap contributes to (N = 96 or 128: the frames are consecutive 32-column
+            // atoms of the B operand, LBO = frame pitch).  The slabs alternate {w_hi, w_lo} tile by tile; four MMA warps take
+            // them round robin -- warp 2 (pair & 1) + lo -- each into its own 128-column accumulator (all 512 TMEM columns; the
+            // epilogue adds the four), so the tensor pipe always has the next warp's instructions queued while one warp
+            // commits and waits for its next slab.  The tape starts with the tap-1 pairs: the first instruction into every
+            // accumulator overwrites all four frame blocks.
             if (tc.warp < 4) {
                 env.tc_fence_after();
 #pragma unroll 1
                 for (int s = 0; s < TP::e0_nslab; s++) {
-                    const int kc = s / 6, jo = (s >> 1) % 3, lo = s & 1;
-                    const int j = (jo == 0) ? 1 : (jo == 1 ? 0 : 2);
-                    if (tc.warp != lo) { env.slab_pass(s); continue; }   // not this warp's slab: only keep the buffer parity in step
+                    const int pr = s >> 1, lo = s & 1;
+                    if (tc.warp != (((pr & 1) << 1) | lo)) { env.slab_pass(s); continue; }   // not this warp's slab: only keep the buffer parity in step
+                    const int kc = TP::e0_pair_kc(pr), j = TP::e0_pair_tap(pr);
                     SVAD_CLK(c0);
                     const float* tile = env.slab_wait(s);
                     SVAD_CLK(c1); SVAD_ACC(11, c1 - c0);
-                    // warp 0 issues the w_hi slabs into D (TMEM columns 0..127), warp 1 the w_lo slabs into a second
-                    // accumulator D2 (columns 256..383) so the two issue streams never touch the same accumulator;
-                    // the epilogue adds them.
                     {
                         const int f0 = (j == 2) ? 1 : 0, t0 = f0 + 1 - j, nf = (j == 1) ? 4 : 3;
+                        const int dcol = lo * 256 + (pr & 1) * 128 + t0 * 32;
                         const auto ad = env.mma_a(tile);
                         const auto bh = env.mma_b(sm + M::mag + (f0 * M::mag_pitch + kc * 32) * kSlots, M::mag_pitch * kSlots * 4);
                         const auto bl = env.mma_b(sm + M::lo0 + (f0 * Kt + kc * 32) * kSlots, Kt * kSlots * 4);
-                        const bool first = (kc == 0) && (jo == 0);
-                        if (!lo) env.template mma_ks4<128, 2>(t0 * 32, ad, bh, ad, bl, ad, bl, !first, 32 * nf);   // w_hi * x_hi, w_hi * x_lo
-                        else env.template mma_ks4<128, 1>(256 + t0 * 32, ad, bh, ad, bh, ad, bh, !first, 32 * nf);   // w_lo * x_hi
+                        const bool first = pr < 2;
+                        if (!lo) env.template mma_ks4<128, 2>(dcol, ad, bh, ad, bl, ad, bl, !first, 32 * nf);   // w_hi * x_hi, w_hi * x_lo
+                        else env.template mma_ks4<128, 1>(dcol, ad, bh, ad, bh, ad, bh, !first, 32 * nf);        // w_lo * x_hi
                         env.mma_slab_done(s);
                     }
                 }
@@ -225,6 +225,14 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     env.tmem_ld16(lq, tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v + 16));
                     env.tmem_ld16(lq, 256 + tt * 32, *reinterpret_cast<float(*)[16]>(v2));
                     env.tmem_ld16(lq, 256 + tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v2 + 16));
+#pragma unroll
+                    for (int s = 0; s < 32; s++) v[s] += v2[s];
+                    env.tmem_ld16(lq, 128 + tt * 32, *reinterpret_cast<float(*)[16]>(v2));
+                    env.tmem_ld16(lq, 128 + tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v2 + 16));
+#pragma unroll
+                    for (int s = 0; s < 32; s++) v[s] += v2[s];
+                    env.tmem_ld16(lq, 384 + tt * 32, *reinterpret_cast<float(*)[16]>(v2));
+                    env.tmem_ld16(lq, 384 + tt * 32 + 16, *reinterpret_cast<float(*)[16]>(v2 + 16));
                     const float* nyq = sm + M::consts + M::c_nyq + tt * kSlots;
                     float lo[32];
 #pragma unroll
