@@ -110,9 +110,10 @@ def cpu_arm(args, threads=None, budget_s=12.0):
     threads = threads or o.best_threads(args.sr)
     n = 512 if args.sr == 16000 else 256
     rng = np.random.default_rng(17 + args.sr)
-    # calibrate: 8 streams/thread x 4 chunks
-    Bs = min(args.batch, 8 * threads)
+    # calibrate: 32 streams/thread x 4 chunks (8 per thread left the OpenMP fork/join and the 4-row GEMM blocks badly amortised)
+    Bs = min(args.batch, 32 * threads)
     x = (rng.standard_normal((Bs, n * 4)) * 0.03).astype(np.float32)
+    o.audio_forward(x, args.sr, nthreads=threads)   # spin the thread pool up
     t0 = time.perf_counter(); o.audio_forward(x, args.sr, nthreads=threads); dt = time.perf_counter() - t0
     rate = Bs * 4 / max(dt, 1e-6)
     T = int(max(4, min(args.chunks, budget_s * rate / Bs)))
@@ -125,7 +126,7 @@ def run_reference(args):
     if rank != 0:
         return
     o, x, T, Bs, threads = cpu_arm(args, budget_s=4.0)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(max(1, min(args.warmup, 3))):
         o.audio_forward(x, args.sr, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
