@@ -123,6 +123,7 @@ struct GpuEnvTC {
     uint64_t* mdone;   // [kTcStages] MMAs that read the stage have completed (tcgen05.commit)
     uint64_t* accb;    // layer accumulators complete
     const float* tape;
+    const int4* tab;   // per slab of a step: {dep_delta | buffer << 8, bytes, shared-memory destination, tape offset} (built once per CTA)
     int tid_;
     uint32_t tmem;
     // warp-0 bookkeeping (identical in all its lanes): next slab to issue / last slab known consumed, their position in
@@ -186,8 +187,16 @@ struct GpuEnvTC {
     __device__ __forceinline__ void ring_freed(int total) {
         using TP = TapeTC<SR16>;
         freed++;
-        while (issued < total && issued - TP::dep_delta(issued_idx) <= freed) {
-            if (elect()) issue(issued_idx);
+        while (issued < total) {
+            const int4 e = tab[issued_idx];   // table lookup: the branchy constexpr slab maps cost the ring warp ~150 cycles per slab
+            if (issued - (e.x & 0xff) > freed) break;
+            if (elect()) {
+                const uint32_t bar = smem_u32(full + (e.x >> 8));
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(e.y) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(e.z),
+                             "l"(tape + e.w), "r"(e.y), "r"(bar)
+                             : "memory");
+            }
             issued++;
             if (++issued_idx == TP::nslab) issued_idx = 0;
         }
@@ -279,7 +288,7 @@ struct GpuEnvTC {
     }
 };
 
-constexpr size_t kSmemBytesTC = (size_t)SmemMapTC::total_floats * 4 + 256;
+constexpr size_t kSmemBytesTC = (size_t)SmemMapTC::total_floats * 4 + 256 + 80 * 16;   // + mbarriers, TMEM slot, slab table
 
 template <bool SR16, int RM, typename S>
 __global__ void __launch_bounds__(kThreads, 1) svad_fused_tc(TileArgs a, int ntiles) {
@@ -288,7 +297,14 @@ __global__ void __launch_bounds__(kThreads, 1) svad_fused_tc(TileArgs a, int nti
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SmemMapTC::total_floats * 4);
     constexpr int NB = TapeTC<SR16>::kBufs;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NB + 2);
-    GpuEnvTC<SR16> env{sm, bars, bars + NB, bars + 2 * NB, a.tape, (int)threadIdx.x, 0u, 0, 0, -2, 0u, 0u, 0u};
+    int4* tab = reinterpret_cast<int4*>(smem_raw + (size_t)SmemMapTC::total_floats * 4 + 256);
+    static_assert(TapeTC<SR16>::nslab <= 80, "slab table size");
+    if ((int)threadIdx.x < TapeTC<SR16>::nslab) {
+        using TP = TapeTC<SR16>;
+        const int i = (int)threadIdx.x, b = TP::buf(i);
+        tab[i] = make_int4(TP::dep_delta(i) | (b << 8), TP::slab_len(i) * 4, (int)smem_u32(sm + TP::template buf_off<SmemMapTC>(b)), TP::slab_off(i));
+    }
+    GpuEnvTC<SR16> env{sm, bars, bars + NB, bars + 2 * NB, a.tape, tab, (int)threadIdx.x, 0u, 0, 0, -2, 0u, 0u, 0u};
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
     if (threadIdx.x == 0) {
