@@ -230,3 +230,17 @@ def test_vad_iterator_batch_equals_independent_iterators():
         want = [single(torch.zeros(512)) for _ in range(T)]
         assert got[b] == want
         assert want == O.vad_iterator_events(probs[:, b].tolist(), 512)
+
+
+def test_hub_entry_point_signature_and_argument_checks():
+    """hubconf.silero_vad mirrors the reference hub entry (hubconf.py:26-56): same parameters, same utils tuple, the
+    reference's exception for an unknown ONNX opset; constructing the engine needs a GPU and must fail loudly without one."""
+    import inspect
+    import hubconf
+    assert list(inspect.signature(hubconf.silero_vad).parameters) == ["onnx", "force_onnx_cpu", "opset_version"]
+    with pytest.raises(Exception, match="Available ONNX opset_version"):
+        hubconf.silero_vad(onnx=True, opset_version=14)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            hubconf.silero_vad()
