@@ -87,8 +87,11 @@ struct SharedTC {
     std::vector<float> tmem;   // [128 lanes][512 columns]
     pthread_barrier_t bar;
     const float* tape;
-    std::atomic<int> landed{0};                      // slabs copied into the ring so far ("full" barriers)
-    std::unique_ptr<std::atomic<int>[]> released;    // per slab: MMA-warp arrivals ("consumed" barriers, 4 expected)
+    // mbarriers, modelled as completed-phase counters: try_wait.parity(P) succeeds once (count & 1) != P, exactly the
+    // hardware rule, and every thread keeps its own parity bits (fpar / mpar) as on the GPU -- so a bookkeeping slip
+    // shows up here as a hang or as a read of a buffer whose copy has not been made yet
+    std::atomic<int> full_c[8];    // "landed": one phase per bulk copy into the buffer
+    std::atomic<int> mdone_c[8];   // "consumed": one phase per tcgen05.commit of the MMA warp that read the buffer
 };
 inline float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 
@@ -106,24 +109,45 @@ struct EmuEnvTC {
     void tc_fence_after() {}
     bool lane0() const { return (tid_ & 31) == 0; }
     using TP = TapeTC<SR16>;
-    int issued_idx = 0, seen = 0;   // ring-warp: per-step index of the next slab to issue; consumers: global index of the next slab to wait for
+    int issued_idx = 0;   // ring warp: per-step index of the next slab to issue
+    uint32_t fpar = 0, mpar = 0;
+    void wait_parity(std::atomic<int>& c, uint32_t parity, const char* what, int idx) {
+        long spins = 0;
+        while ((uint32_t)(c.load(std::memory_order_acquire) & 1) == parity) {
+            sched_yield();
+            if (++spins == 200000000L) {   // a hang is a bookkeeping bug: say where, then die so the test fails fast
+                fprintf(stderr, "svad_emu: thread %d stuck waiting for %s of slab %d (count %d, parity %u)\n", tid_, what, idx, c.load(), parity);
+                abort();
+            }
+        }
+    }
     void issue(int idx) {
-        memcpy(sh->smem.data() + TP::template buf_off<SmemMapTC>(TP::buf(idx)), sh->tape + TP::slab_off(idx), sizeof(float) * TP::slab_len(idx));
+        const int b = TP::buf(idx);
+        memcpy(sh->smem.data() + TP::template buf_off<SmemMapTC>(b), sh->tape + TP::slab_off(idx), sizeof(float) * TP::slab_len(idx));
+        sh->full_c[b].fetch_add(1, std::memory_order_release);
     }
     const float* slab_wait(int idx) {
-        while (sh->landed.load(std::memory_order_acquire) <= seen) sched_yield();
-        seen++;
-        return sh->smem.data() + TP::template buf_off<SmemMapTC>(TP::buf(idx));
+        const int b = TP::buf(idx);
+        // the lanes of a warp run in lockstep on the GPU; here they are free-running OS threads, and a lane that lags by two
+        // phases would misread the parity.  Only lane 0 consumes the slab (it issues the MMAs), so only lane 0 waits.
+        if (lane0()) wait_parity(sh->full_c[b], (fpar >> b) & 1u, "landed", idx);
+        fpar ^= 1u << b;
+        return sh->smem.data() + TP::template buf_off<SmemMapTC>(b);
     }
-    void skip_phase(uint32_t, int n) { seen += n; }
-    void slab_pass(int) { seen++; }
-    void wait_consumed_group(int, int n) {   // the next n slabs to be freed are MMA slabs: wait for the consumer's arrival on the last
-        while (sh->released[freed + n].load(std::memory_order_acquire) < 1) sched_yield();
+    void skip_phase(uint32_t mask, int) { fpar ^= mask; }
+    void slab_pass(int idx) { fpar ^= 1u << TP::buf(idx); }
+    void wait_consumed_group(int idx, int n) {
+        if (!lane0()) return;   // as above: lane 0 stands for the (lockstep) ring warp
+        for (int i = 0; i < n - 1; i++) mpar ^= 1u << TP::buf(idx + i);
+        const int b = TP::buf(idx + n - 1);
+        wait_parity(sh->mdone_c[b], (mpar >> b) & 1u, "consumed", idx + n - 1);
+        mpar ^= 1u << b;
     }
     void ring_freed(int total) {
+        if (!lane0()) return;
         freed++;
         while (issued < total && issued - TP::dep_delta(issued_idx) <= freed) {
-            if (lane0()) { issue(issued_idx); sh->landed.store(issued + 1, std::memory_order_release); }
+            issue(issued_idx);
             issued++;
             if (++issued_idx == TP::nslab) issued_idx = 0;
         }
@@ -160,8 +184,7 @@ struct EmuEnvTC {
             if (NP >= 3) mma<MM>(col, a2, b2, ks, true, ncols12);
         }
     }
-    void mma_slab_done(int) { if (lane0()) sh->released[seen - 1].fetch_add(1, std::memory_order_acq_rel); }
-    void slab_skip(int) { if (lane0()) sh->released[seen - 1].fetch_add(1, std::memory_order_acq_rel); }
+    void mma_slab_done(int idx) { if (lane0()) sh->mdone_c[TP::buf(idx)].fetch_add(1, std::memory_order_acq_rel); }
     void acc_commit() {}
     void acc_wait() { pthread_barrier_wait(&sh->bar); }
     void tmem_ld16(int lq, int col, float (&v)[16]) {
@@ -178,8 +201,7 @@ void run_tc(const TileArgs& a, int ntiles) {
     sh.tape = a.tape;
     pthread_barrier_init(&sh.bar, nullptr, kThreads);
     const int total = (int)((long)ntiles * a.T * TapeTC<SR16>::nslab);
-    sh.released.reset(new std::atomic<int>[total + 1]);
-    for (int i = 0; i <= total; i++) sh.released[i] = 0;
+    for (int i = 0; i < 8; i++) { sh.full_c[i] = 0; sh.mdone_c[i] = 0; }
     EmuEnvTC<SR16> boot{&sh, 0};
     boot.freed = -2;
     boot.ring_freed(total);   // freed = -1: primes every buffer whose first slab has no predecessor
