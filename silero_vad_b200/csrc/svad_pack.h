@@ -154,14 +154,18 @@ inline bool pack_branch(const TensorMap& tm, PackedBranch& out, std::string& err
 }
 
 // ---------------------------------------------------------------- tensor-core tape (svad_tc.h)
-// enc0 and the LSTM run on tcgen05 (kind::tf32, M=128 weights x N=32 stream slots x K=8), split precision
+// Every dense layer runs on tcgen05 (kind::tf32, weights = M operand, stream slots = N, K = 8), split precision
 //   x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo,   hi = fp32 value as is (the tensor core TRUNCATES fp32 containers to
-// tf32: tools/umma_unit.cu), lo = v - trunc_tf32(v) (exact in fp32).  A weight slab is one [128 rows x 32 k] tile pair
-// {hi | lo} in the K-major SWIZZLE_128B canonical layout (row r at (r/8)*1024 + (r%8)*128 B, 16-byte chunk (k/4)^(r%8)):
-//   enc0  for kc < Kt/32, tap j in (1, 0, 2) : rows o < 128, k = bins kc*32..+32 of W0[o][bin][j]     (Kt = 128 / 64)
-//         (the Nyquist bin F-1 is added on the CUDA cores from consts c_wnyq, a rank-1 update)
-//   enc1-3  as in Tape<> (CUDA-core layers)
-//   lstm  for kc < 8, gate block m < 4 : rows j < 128 (hidden unit), k = kc*32..+32 of [W_ih ; W_hh][m*128 + j][k]
+// tf32: tools/umma_unit.cu), lo = v - trunc_tf32(v) (exact in fp32).  A weight slab holds K-major SWIZZLE_128B tiles
+// (row r at (r/8)*1024 + (r%8)*128 B, 16-byte chunk (k/4)^(r%8)); slabs in consumption order:
+//   enc0  24 / 12 slabs of 16 KB: [128 x 32] tiles, {hi, lo} alternating; pairs ordered tap 1 of every k-chunk first, then
+//         taps 0, 2 chunk by chunk (e0_pair_kc / e0_pair_tap); rows o < 128, k = bins kc*32..+32 of W0[o][bin][tap]
+//         (Kt = 128 / 64 bins; the Nyquist bin F-1 is a rank-1 update on the CUDA cores from consts c_wnyq)
+//   enc1  12 slabs of 16 KB: [64 x 32] tiles {hi | lo}; taps in order 1, 2, 0, k-chunk kc < 4 of W1[o][c][tap]
+//   enc2  4 slabs: [64 x 32] {hi | lo}; q = (tap - 1) * 2 + channel half of W2[o][c][tap], taps 1, 2
+//   enc3  4 slabs: [128 x 32] tiles, (kc, hi | lo) of W3[o][c][tap 1]
+//   lstm  32 slabs of 32 KB: [128 x 32] tile pairs {hi | lo}; for kc < 8, gate block m < 4: rows j < 128 (hidden unit),
+//         k = kc*32..+32 of [W_ih ; W_hh][m*128 + j][k]
 template <bool SR16>
 struct TapeTC {
     using G = Geo<SR16>;

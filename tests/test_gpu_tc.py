@@ -1,4 +1,4 @@
-"""GPU parity of the tensor-core kernel (tcgen05, split-precision TF32 for enc0 + LSTM) against the reference goldens,
+"""GPU parity of the tensor-core kernel (tcgen05, split-precision TF32 for all dense layers) against the reference goldens,
 the oracle and the fp32 CUDA-core kernel.  Same tolerances as test_gpu_parity.py."""
 import numpy as np
 import pytest
