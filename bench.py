@@ -31,6 +31,9 @@ sys.path.insert(0, str(REPO))
 ALGO_BYTES = {16000: 2052, 8000: 1028}          # audio fp32 in + prob fp32 out, per chunk
 ALGO_FLOP = {16000: 0.730e6, 8000: 0.553e6}     # algorithmic minimum FLOP per chunk (rFFT, dead taps skipped)
 HBM_FALLBACK_GBS = 6650.0                       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# MACs of the four convolutions + LSTM that the tensor-core kernel runs on tcgen05 (everything but the Nyquist bin and the head)
+TENSOR_MAC = {16000: 352256, 8000: 270336}   # 353 664 - 1 280 (Nyquist bin) - 128 (head); 271 744 - 1 280 - 128
+BF16_FALLBACK_TFLOPS = 2250.0                   # nominal dense bf16 peak when MEASURED_PEAKS.json is absent
 
 
 def parse():
@@ -54,6 +57,15 @@ def peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def bf16_peak():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return BF16_FALLBACK_TFLOPS, "nominal (2.25 PFLOP/s dense bf16)"
 
 
 class ClockSampler:
@@ -265,21 +277,32 @@ def run_b200(args):
             traffic = None
     out = {
         "metric": "chunks/sec", "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32x3" if args.kernel == "tc" else "f32",   # tf32x3 = 3-product hi/lo split on tcgen05, fp32 accumulate (fp32-class results)
         "data": "synthetic",
         "config": {"workload": f"batch={B} independent {sr} Hz streams per GPU x {T} chunks per step (BASELINE configs[2])",
                    "sr": sr, "batch_per_gpu": B, "chunks_per_stream": T, "global_streams": B * world,
                    "l2": "inputs (%.0f MB/step/GPU) larger than L2, no flush needed" % (B * L * 4 / 1e6),
                    "parallelism": f"dp{world}: streams sharded, weights replicated, NCCL all-gather of probabilities" if world > 1 else "single GPU",
-                   "kernel": ("svad_fused_tc (tcgen05 split-TF32 for enc0-3 + LSTM; STFT, gate math and head on the CUDA cores)" if args.kernel == "tc" else "svad_fused_fp32 (fp32 FFMA2, CUDA cores only)")},
+                   "kernel": ("svad_fused_tc (tcgen05 split-TF32 for enc0-3 + LSTM; STFT, gate math and head on the CUDA cores)" if args.kernel == "tc" else "svad_fused_fp32 (fp32 FFMA2, CUDA cores only)"),
+                   "precision": ("x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in tf32 with fp32 accumulate; probabilities within 7e-6 of the fp32 reference" if args.kernel == "tc" else "IEEE fp32")},
         "gpu_launches": int(launches),
         "kernel_ms": kernel_ms,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_chunk": ALGO_BYTES[sr],
                      "fp32_frac": achieved_flops / fp32_peak_now, "fp32_frac_of_max_clock": achieved_flops / fp32_peak_max,
-                     "fp32_note": "binding pipe is fp32 FMA (356 FLOP/B vs ridge ~11): algorithmic 0.73 MFLOP/chunk over SMs*128*2*clock"},
+                     "fp32_note": "the path is compute-bound (356 FLOP/B vs ridge ~11); fp32_frac = algorithmic 0.73 MFLOP/chunk over "
+                                  "SMs*128*2*clock, the CUDA-core FMA roofline an all-fp32 implementation is held to"},
     }
+    if args.kernel == "tc":
+        # second view for the tensor-core kernel: what it executes on tcgen05 vs the tensor peak.  tf32 runs at half the bf16
+        # rate and split precision issues 3 products per MAC, so 1/6 of the bf16 peak is the ceiling for algorithmic FLOP.
+        bf16, bf16_src = bf16_peak()
+        algo_t = 2.0 * TENSOR_MAC[sr] * B * T / (kernel_ms * 1e-3) / 1e12
+        out["roofline"]["tensor"] = {"algorithmic_tflops": algo_t, "executed_tf32_tflops": 3.0 * algo_t, "peak_bf16_tflops": bf16,
+                                     "peak_source": bf16_src, "frac_of_tf32_peak": 3.0 * algo_t / (0.5 * bf16),
+                                     "note": "dense-layer MACs on tcgen05 (x3 products of the hi/lo split) over half the bf16 peak (tf32 rate)"}
     if e2e:
         out["e2e"] = e2e
     if world == 1:
