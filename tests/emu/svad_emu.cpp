@@ -231,11 +231,10 @@ extern "C" int svad_emu_forward_tc(const char* weights, int sr, int rm, int B, l
     a.state_in = state_in; a.ctx_in = ctx_in; a.ctx_ld = sr16 ? 64 : 32; a.state_out = state_out; a.ctx_out = ctx_out;
     a.probs = probs; a.ldp = a.T; a.tape = pb.tape.data(); a.consts = pb.consts.data();
     const int bt = 4 * rm, ntiles = (B + bt - 1) / bt;
-    if (pcm16) return -4;
-    if (sr16 && rm == 8) run_tc<true, 8, float>(a, ntiles);
-    else if (sr16 && rm == 7) run_tc<true, 7, float>(a, ntiles);
-    else if (!sr16 && rm == 8) run_tc<false, 8, float>(a, ntiles);
-    else if (!sr16 && rm == 7) run_tc<false, 7, float>(a, ntiles);
+    if (sr16 && rm == 8) pcm16 ? run_tc<true, 8, int16_t>(a, ntiles) : run_tc<true, 8, float>(a, ntiles);
+    else if (sr16 && rm == 7) pcm16 ? run_tc<true, 7, int16_t>(a, ntiles) : run_tc<true, 7, float>(a, ntiles);
+    else if (!sr16 && rm == 8) pcm16 ? run_tc<false, 8, int16_t>(a, ntiles) : run_tc<false, 8, float>(a, ntiles);
+    else if (!sr16 && rm == 7) pcm16 ? run_tc<false, 7, int16_t>(a, ntiles) : run_tc<false, 7, float>(a, ntiles);
     else return -3;
     return 0;
 }

@@ -161,6 +161,35 @@ def test_emulated_tensor_core_kernel_matches_oracle(emu, oracle, fixtures, sr, r
     assert np.array_equal(cx_e, cx_o)
 
 
+@pytest.mark.parametrize("sr,L", [(16000, 300), (16000, 700), (8000, 256)])
+def test_emulated_tensor_core_kernel_short_streams(emu, oracle, fixtures, sr, L):
+    """One- and two-chunk streams through the tensor-core schedule: no next chunk to prefetch, zero-padded tail, zero initial
+    state (null pointers), the weight stream wound up after a single step."""
+    from silero_vad_b200.model import WEIGHTS
+    a = fixtures["test16k"]["audio"]
+    x = np.stack([a[40000 + 7000 * b:][:L] for b in range(3)]).copy()
+    want = oracle.audio_forward(x, sr, nthreads=2)
+    probs = np.zeros_like(want)
+    st_e = np.zeros((2, 3, 128), np.float32)
+    rc = emu.svad_emu_forward_tc(str(WEIGHTS).encode(), sr, 8, 3, L, x.ctypes.data, 0, None, None, st_e.ctypes.data, None, probs.ctypes.data)
+    assert rc == 0
+    assert np.abs(probs - want).max() < 2e-5
+
+
+def test_emulated_tensor_core_kernel_pcm16_equals_f32(emu, fixtures):
+    """int16 PCM ingest of the tensor-core schedule: bit-identical to feeding int16/32768 as fp32 (rows of 7-row tiles)."""
+    from silero_vad_b200.model import WEIGHTS
+    pcm = np.stack([fixtures["test16k"]["pcm"][20000 * b: 20000 * b + 512 * 3 + 100] for b in range(3)]).copy()
+    f32 = pcm.astype(np.float32) / 32768.0
+    out = []
+    for arr, flag in ((f32, 0), (pcm, 1)):
+        p = np.zeros((3, 4), np.float32)
+        assert emu.svad_emu_forward_tc(str(WEIGHTS).encode(), 16000, 7, 3, arr.shape[1], arr.ctypes.data, flag, None, None, None, None,
+                                       p.ctypes.data) == 0
+        out.append(p)
+    assert np.array_equal(out[0], out[1]) and out[0].max() > 0.5
+
+
 def test_emulated_kernel_pcm16_equals_f32(emu, fixtures):
     """int16 PCM ingest (scaled by 2^-15 on load) must be bit-identical to feeding int16/32768 as fp32."""
     from silero_vad_b200.model import WEIGHTS
