@@ -321,3 +321,26 @@ def make_visualization(probs, step):
     pd.DataFrame({'probs': probs}, index=[x * step for x in range(len(probs))]).plot(
         figsize=(16, 8), kind='area', ylim=[0, 1.05], xlim=[0, len(probs) * step], xlabel='seconds',
         ylabel='speech probability', colormap='tab20')
+
+
+# ---- constructors of the reference's two model classes (utils_vad.py:10-31, 194-199), for callers that build the model
+# themselves instead of going through load_silero_vad().  Both return the CUDA engine; the model file path is accepted and
+# ignored (the weights are the ones of silero_vad.jit), and there is no CPU execution to force.
+def init_jit_model(model_path: str = None, device=None):
+    """Reference: utils_vad.py:194-199 (torch.jit.load + eval).  `device`: a CUDA device / index, default cuda:0."""
+    del model_path
+    if isinstance(device, torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("silero_vad_b200 runs on a CUDA device only (no CPU fallback)")
+        device = device.index or 0
+    return SileroVADB200(device=device)
+
+
+class OnnxWrapper(SileroVADB200):
+    """Reference: utils_vad.py:10-31.  Same call protocol as the TorchScript wrapper; `force_onnx_cpu` has no meaning here."""
+
+    def __init__(self, path=None, force_onnx_cpu=False):
+        del force_onnx_cpu
+        super().__init__()
+        if path is not None and "16k" in str(path):
+            self.sample_rates = [16000]   # silero_vad_16k_op15.onnx is 16 kHz only (utils_vad.py:27-29)

@@ -273,3 +273,15 @@ def test_hub_entry_point_signature_and_argument_checks():
     if not torch.cuda.is_available():
         with pytest.raises(Exception):
             hubconf.silero_vad()
+
+
+def test_reference_model_constructors_exist():
+    """utils_vad.init_jit_model / OnnxWrapper (reference utils_vad.py:10-31, 194-199) exist with the reference's parameters and
+    refuse a CPU device instead of falling back."""
+    import inspect
+    import torch
+    from silero_vad_b200 import utils_vad as U
+    assert list(inspect.signature(U.init_jit_model).parameters) == ["model_path", "device"]
+    assert list(inspect.signature(U.OnnxWrapper.__init__).parameters) == ["self", "path", "force_onnx_cpu"]
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        U.init_jit_model("silero_vad.jit", torch.device("cpu"))
