@@ -76,6 +76,14 @@ int svad_forward_device_pcm16(svad_engine* e, int sr, int B, int64_t L, int64_t 
                               const float* d_state_in, const float* d_ctx_in, float* d_state_out, float* d_ctx_out,
                               float* d_probs, int64_t ldp, void* stream);
 
+/* General form of the two calls above.  sample_format: 0 = f32, 1 = int16 PCM.  sample_stride k >= 1: rows hold
+ * sr_in = k * sr audio and the kernel reads every k-th stored sample -- the reference's `x[:, ::step]` decimation for
+ * sampling rates that are a multiple of 16000 (src/silero_vad/utils_vad.py:39-42, 301-305) done by the load itself.
+ * L counts STORED samples per row; the model sees ceil(L / k) of them. */
+int svad_forward_device_ex(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const void* d_audio, int sample_format,
+                           int sample_stride, const float* d_state_in, const float* d_ctx_in, float* d_state_out,
+                           float* d_ctx_out, float* d_probs, int64_t ldp, void* stream);
+
 /* One chunk, the stateless ONNX contract (utils_vad.py:80-82; examples/cpp/silero-vad-onnx.cpp:176-195):
  *   d_input f32[B][ctx+n] (context already prepended), d_state_in f32[2][B][128] (NULL = zeros)
  *   -> d_prob f32[B], d_state_out f32[2][B][128] (may alias d_state_in). */
@@ -115,6 +123,18 @@ void svad_segment_params_default(svad_segment_params* p);
 int svad_speech_segments(const float* probs, int64_t B, int64_t T, int64_t ldp, const int64_t* audio_len,
                          const svad_segment_params* p, int64_t* seg_offsets, int64_t* seg_bounds, int64_t cap,
                          int64_t* n_total);
+
+/* ---- collect_chunks / drop_chunks as ONE device gather ------------------------------------------------
+ * Replaces: src/silero_vad/utils_vad.py:552-646 (`torch.cat([wav[s:e] for ...])` / its complement), batched over B rows
+ * so that speech-only audio stays on the GPU for a downstream stage.
+ *   d_wav       [B][ld] elements of elem_bytes (4 = f32, 2 = int16 PCM); row_len[B] (host) valid samples per row
+ *   seg_rows[n], seg_bounds[n][2] (host): segment k = samples [start, end) of row seg_rows[k]; rows non-decreasing; bounds
+ *               are clamped to the row length like Python slices; drop != 0 gathers what lies BETWEEN the segments
+ *               (wav[cur:start], cur = end, ..., wav[cur:]) exactly like drop_chunks
+ *   d_out       out_cap elements or NULL (sizing pass); out_offsets[B+1] (host) = per-row prefix sums of the output */
+int svad_collect_chunks_device(svad_engine* e, const void* d_wav, int elem_bytes, int64_t B, int64_t ld, const int64_t* row_len,
+                               const int64_t* seg_rows, const int64_t* seg_bounds, int64_t n_seg, int drop, void* d_out,
+                               int64_t out_cap, int64_t* out_offsets, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,8 +9,8 @@
 __version__ = "0.1.0"
 
 from .model import SileroVADB200, load_silero_vad
-from .utils_vad import (VADIterator, VADIteratorBatch, collect_chunks, drop_chunks, get_speech_timestamps,
+from .utils_vad import (VADIterator, VADIteratorBatch, collect_chunks, collect_chunks_batch, drop_chunks, get_speech_timestamps,
                         get_speech_timestamps_batch, read_audio, save_audio)
 
 __all__ = ["SileroVADB200", "load_silero_vad", "get_speech_timestamps", "get_speech_timestamps_batch", "VADIterator", "VADIteratorBatch",
-           "collect_chunks", "drop_chunks", "read_audio", "save_audio"]
+           "collect_chunks", "collect_chunks_batch", "drop_chunks", "read_audio", "save_audio"]

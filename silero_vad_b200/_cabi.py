@@ -12,7 +12,8 @@ _lib = None
 
 EXPORTS = ["svad_abi_version", "svad_last_error", "svad_engine_create", "svad_engine_destroy",
            "svad_engine_set_tile_rows", "svad_engine_set_kernel", "svad_engine_set_small_batch_max", "svad_engine_sm_count", "svad_engine_launch_count",
-           "svad_forward_device", "svad_forward_device_pcm16", "svad_step_device", "svad_forward_host",
+           "svad_forward_device", "svad_forward_device_pcm16", "svad_forward_device_ex", "svad_step_device", "svad_forward_host",
+           "svad_collect_chunks_device",
            "svad_forward_host_pcm16", "svad_step_host",
            "svad_segment_params_default", "svad_speech_segments"]
 
@@ -34,9 +35,9 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = Path(LIB)
-    if not path.exists():
-        path = build()
+    # build() compares a content hash of csrc/ + include/ with the one the library was built from and recompiles on a
+    # mismatch, so Python never loads a library whose ABI or weight-tape layout differs from the sources in the tree
+    path = Path(build())
     L = ctypes.CDLL(str(path))
     i64, i32, vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
     L.svad_abi_version.restype = i32
@@ -53,6 +54,8 @@ def lib():
     L.svad_forward_device.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]
     L.svad_forward_device_pcm16.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]
     L.svad_forward_host_pcm16.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64]
+    L.svad_forward_device_ex.argtypes = [vp, i32, i32, i64, i64, vp, i32, i32, vp, vp, vp, vp, vp, i64, vp]
+    L.svad_collect_chunks_device.argtypes = [vp, vp, i32, i64, i64, vp, vp, vp, i64, i32, vp, i64, vp, vp]
     L.svad_step_device.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.svad_forward_host.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64]
     L.svad_step_host.argtypes = [vp, i32, i32, vp, vp, vp, vp]
@@ -111,6 +114,24 @@ class Engine:
 
     def forward_device_pcm16(self, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream=0):
         check(lib().svad_forward_device_pcm16(self._h, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream))
+
+    def forward_device_ex(self, sr, B, L, ld, audio, sample_format, sample_stride, state_in, ctx_in, state_out, ctx_out, probs, ldp, stream=0):
+        """sample_format 0 = f32, 1 = int16 PCM; sample_stride k reads every k-th stored sample (sr = k * 16000 input)."""
+        check(lib().svad_forward_device_ex(self._h, sr, B, L, ld, audio, sample_format, sample_stride, state_in, ctx_in, state_out,
+                                           ctx_out, probs, ldp, stream))
+
+    def collect_chunks_device(self, wav_ptr, elem_bytes, B, ld, row_len, seg_rows, seg_bounds, drop, out_ptr, out_cap, stream=0):
+        """One gather launch over a segment table (svad_collect_chunks_device); returns out_offsets[B+1] (numpy int64).
+        out_ptr = 0 only sizes the result."""
+        import numpy as np
+        row_len = np.ascontiguousarray(row_len, np.int64)
+        seg_rows = np.ascontiguousarray(seg_rows, np.int64)
+        seg_bounds = np.ascontiguousarray(seg_bounds, np.int64).reshape(-1, 2)
+        offs = np.zeros(B + 1, np.int64)
+        check(lib().svad_collect_chunks_device(self._h, wav_ptr, elem_bytes, B, ld, row_len.ctypes.data, seg_rows.ctypes.data,
+                                               seg_bounds.ctypes.data, len(seg_rows), 1 if drop else 0, out_ptr, out_cap,
+                                               offs.ctypes.data, stream))
+        return offs
 
     def forward_host_pcm16(self, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp):
         check(lib().svad_forward_host_pcm16(self._h, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp))

@@ -2,6 +2,7 @@
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the tree.
 """
+import hashlib
 import os
 import shutil
 import subprocess
@@ -12,7 +13,8 @@ LIB = PKG / "lib" / "libsilero_vad_b200.so"
 SOURCES = [PKG / "csrc" / "svad_api.cu", PKG / "csrc" / "svad_segments.cpp"]
 HEADERS = sorted((PKG / "csrc").glob("*.h")) + [PKG.parent / "include" / "silero_vad_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xptxas", "-v"]
+HASH = PKG / "lib" / "source_hash.txt"
 
 
 def nvcc_path():
@@ -22,11 +24,19 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def source_hash():
+    """sha256 over the sources, headers and flags the library is built from (content, not mtimes: the tree is copied
+    to the GPU box, where file times say nothing)."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in sorted(SOURCES + HEADERS):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
 def stale():
-    if not LIB.exists():
-        return True
-    t = LIB.stat().st_mtime
-    return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
+    """True when the library is missing or was built from other sources than the ones in the tree."""
+    return not (LIB.exists() and HASH.exists() and HASH.read_text().strip() == source_hash())
 
 
 def build(force=False, verbose=False):
@@ -40,6 +50,7 @@ def build(force=False, verbose=False):
         if r.returncode:
             raise RuntimeError("nvcc failed building %s" % LIB)
         (PKG / "lib" / "ptxas.log").write_text(r.stderr)
+        HASH.write_text(source_hash() + "\n")
     return LIB
 
 

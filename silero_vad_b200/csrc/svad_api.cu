@@ -13,8 +13,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/silero_vad_b200.h"
 #include "svad_tc.h"
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs 
         for (int i = tid; i < (G::L1 + G::N / 4) * 4; i += kSmallThreads) {
             const int k = i >> 2, st = i & 3, g = g0 + st;
             float v = 0.0f;
-            if (g < a.B) v = window_sample<SR16, S>(audio + (long)g * a.ld, a.L, a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr, t, k);
+            if (g < a.B) v = window_sample<SR16, S>(audio + (long)g * a.ld, a.L, a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr, t, k, a.dec);
             sm[M::a_xp + i] = v;
         }
         __syncthreads();
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs 
             const int st = i / G::ctx, k = i % G::ctx, g = g0 + st;
             if (g < a.B) {
                 const float* cx = a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr;
-                a.ctx_out[(long)g * G::ctx + k] = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k) : (cx ? cx[k] : 0.0f);
+                a.ctx_out[(long)g * G::ctx + k] = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k, a.dec) : (cx ? cx[k] : 0.0f);
             }
         }
     }
@@ -613,19 +615,32 @@ constexpr int kMaxSlices = 8;
 extern "C" int svad_abi_version(void) { return 1; }
 extern "C" const char* svad_last_error(void) { return g_err.c_str(); }
 
+static int engine_upload(svad_engine* e, int device, int sms, const TensorMap& tm, PackedBranch* pb, PackedBranch* pbt);
+static int engine_create_impl(const char* weights_path, int device, svad_engine** out);
+
 extern "C" int svad_engine_create(const char* weights_path, int device, svad_engine** out) {
+    try {
+        return engine_create_impl(weights_path, device, out);
+    } catch (const std::bad_alloc&) {
+        return fail(SVAD_ENOMEM, "out of memory while loading %s", weights_path ? weights_path : "(null)");
+    } catch (const std::exception& ex) {
+        return fail(SVAD_EWEIGHTS, "%s", ex.what());
+    }
+}
+
+static int engine_create_impl(const char* weights_path, int device, svad_engine** out) {
     if (!weights_path || !out) return fail(SVAD_EINVAL, "null argument");
     *out = nullptr;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail(SVAD_ECUDA, "no CUDA device: silero_vad_b200 has no CPU fallback");
-    if (device < 0 || device >= ndev) return fail(SVAD_EINVAL, "device %d out of range (%d devices)", device, ndev);
     TensorMap tm;
     std::string err;
     if (!read_container(weights_path, tm, err)) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
     PackedBranch pb[2], pbt[2];
     if (!pack_branch<true>(tm, pb[0], err) || !pack_branch<false>(tm, pb[1], err)) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
     if (!pack_branch_tc<true>(tm, pbt[0], err) || !pack_branch_tc<false>(tm, pbt[1], err)) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SVAD_ECUDA, "no CUDA device: silero_vad_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SVAD_EINVAL, "device %d out of range (%d devices)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -633,8 +648,15 @@ extern "C" int svad_engine_create(const char* weights_path, int device, svad_eng
         return fail(SVAD_ECUDA, "device offers %zu B shared memory per block, kernel needs %zu", (size_t)prop.sharedMemPerBlockOptin, kSmemBytes);
     svad_engine* e = new (std::nothrow) svad_engine();
     if (!e) return fail(SVAD_ENOMEM, "out of memory");
+    const int rc = engine_upload(e, device, prop.multiProcessorCount, tm, pb, pbt);
+    if (rc != SVAD_OK) { svad_engine_destroy(e); return rc; }   // every partially created resource is released
+    *out = e;
+    return SVAD_OK;
+}
+
+static int engine_upload(svad_engine* e, int device, int sms, const TensorMap& tm, PackedBranch* pb, PackedBranch* pbt) {
     e->device = device;
-    e->sms = prop.multiProcessorCount;
+    e->sms = sms;
     for (int b = 0; b < 2; b++) {
         CUDA_TRY(cudaMalloc(&e->d_tape[b], pb[b].tape.size() * 4));
         CUDA_TRY(cudaMalloc(&e->d_consts[b], pb[b].consts.size() * 4));
@@ -652,7 +674,6 @@ extern "C" int svad_engine_create(const char* weights_path, int device, svad_eng
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream_copy, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxSlices; i++) CUDA_TRY(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
-    *out = e;
     return SVAD_OK;
 }
 
@@ -781,20 +802,22 @@ static int launch_rm(svad_engine* e, const TileArgs& a, cudaStream_t st) {
 enum SampleFmt { kF32 = 0, kI16 = 1 };
 static size_t fmt_size(int fmt) { return fmt == kI16 ? 2 : 4; }
 
-static int forward_impl(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const void* d_audio, int fmt, const float* d_state_in,
+// `Lraw` stored samples per row, of which every `dec`-th is read: the model sees L = ceil(Lraw / dec) samples (x[:, ::dec]).
+static int forward_impl(svad_engine* e, int sr, int B, int64_t Lraw, int64_t ld, const void* d_audio, int fmt, const float* d_state_in,
                         const float* d_ctx_in, int64_t ctx_ld, float* d_state_out, float* d_ctx_out, float* d_probs,
-                        int64_t ldp, cudaStream_t st) {
+                        int64_t ldp, cudaStream_t st, int dec = 1) {
     if (!e) return fail(SVAD_EINVAL, "null engine");
     if (sr != 16000 && sr != 8000) return fail(SVAD_EINVAL, "Supported sampling rates: [8000, 16000] (got %d)", sr);
-    if (B < 0 || L < 0) return fail(SVAD_EINVAL, "negative size");
+    if (B < 0 || Lraw < 0 || dec < 1) return fail(SVAD_EINVAL, "negative size");
+    const int64_t L = (Lraw + dec - 1) / dec;
     const int n = sr == 16000 ? 512 : 256;
     const int64_t T = (L + n - 1) / n;
     if (B == 0 || (T == 0 && !d_state_out && !d_ctx_out)) return SVAD_OK;
-    if ((T > 0 && (!d_audio || !d_probs)) || ld < L || ldp < T) return fail(SVAD_EINVAL, "bad audio/probs pointer or stride");
+    if ((T > 0 && (!d_audio || !d_probs)) || ld < Lraw || ldp < T) return fail(SVAD_EINVAL, "bad audio/probs pointer or stride");
     CUDA_TRY(cudaSetDevice(e->device));
     const int br = sr == 16000 ? 0 : 1;
     TileArgs a{};
-    a.audio = d_audio; a.ld = ld; a.L = L; a.B = B; a.T = T;
+    a.audio = d_audio; a.ld = ld; a.L = L; a.dec = dec; a.B = B; a.T = T;
     a.state_in = d_state_in; a.ctx_in = d_ctx_in; a.ctx_ld = ctx_ld;
     a.state_out = d_state_out; a.ctx_out = d_ctx_out;
     a.probs = d_probs; a.ldp = ldp; a.dbg = e->dbg;
@@ -816,6 +839,16 @@ extern "C" int svad_forward_device_pcm16(svad_engine* e, int sr, int B, int64_t 
                                          float* d_probs, int64_t ldp, void* stream) {
     return forward_impl(e, sr, B, L, ld, d_audio, kI16, d_state_in, d_ctx_in, sr == 16000 ? 64 : 32, d_state_out, d_ctx_out,
                         d_probs, ldp, (cudaStream_t)stream);
+}
+
+// sample_format: 0 = f32, 1 = int16 PCM; sample_stride k >= 1 reads every k-th stored sample (sr = k * 16000 input).
+extern "C" int svad_forward_device_ex(svad_engine* e, int sr, int B, int64_t L, int64_t ld, const void* d_audio, int sample_format,
+                                      int sample_stride, const float* d_state_in, const float* d_ctx_in, float* d_state_out,
+                                      float* d_ctx_out, float* d_probs, int64_t ldp, void* stream) {
+    if (sample_format != kF32 && sample_format != kI16) return fail(SVAD_EINVAL, "sample_format must be 0 (f32) or 1 (int16 PCM)");
+    if (sample_stride < 1) return fail(SVAD_EINVAL, "sample_stride must be >= 1");
+    return forward_impl(e, sr, B, L, ld, d_audio, sample_format, d_state_in, d_ctx_in, sr == 16000 ? 64 : 32, d_state_out, d_ctx_out,
+                        d_probs, ldp, (cudaStream_t)stream, sample_stride);
 }
 
 extern "C" int svad_step_device(svad_engine* e, int sr, int B, const float* d_input, const float* d_state_in, float* d_prob,
@@ -960,4 +993,89 @@ extern "C" int svad_step_host(svad_engine* e, int sr, int B, const float* input,
     memcpy(prob, hp + o_prob, (size_t)B * 4);
     if (state_out) memcpy(state_out, hp + o_state, (size_t)2 * B * 128 * 4);
     return SVAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------ collect_chunks / drop_chunks
+// One gather launch over a segment table (reference: src/silero_vad/utils_vad.py:552-646, `torch.cat([wav[s:e] ...])`).
+// plan[i] = {source element offset, destination element offset, length}; a CTA takes 8192 consecutive output elements,
+// finds its first piece by bisection (once, thread 0) and walks forward: reads and writes are coalesced, HBM-bound.
+namespace {
+constexpr int kGatherUnit = 8192;
+template <typename E>
+__global__ void __launch_bounds__(256) svad_gather_segments(const E* __restrict__ src, E* __restrict__ dst, const long long* __restrict__ plan,
+                                                            long long npieces, long long total) {
+    __shared__ long long s_first;
+    for (long long i0 = (long long)blockIdx.x * kGatherUnit; i0 < total; i0 += (long long)gridDim.x * kGatherUnit) {
+        if (threadIdx.x == 0) {
+            long long lo = 0, hi = npieces - 1;   // last piece whose destination offset is <= i0
+            while (lo < hi) {
+                const long long mid = (lo + hi + 1) >> 1;
+                if (plan[3 * mid + 1] <= i0) lo = mid; else hi = mid - 1;
+            }
+            s_first = lo;
+        }
+        __syncthreads();
+        long long pc = s_first;
+        const long long iend = i0 + kGatherUnit < total ? i0 + kGatherUnit : total;
+        for (long long i = i0 + threadIdx.x; i < iend; i += blockDim.x) {
+            while (pc + 1 < npieces && plan[3 * (pc + 1) + 1] <= i) pc++;
+            dst[i] = src[plan[3 * pc] + (i - plan[3 * pc + 1])];
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+extern "C" int svad_collect_chunks_device(svad_engine* e, const void* d_wav, int elem_bytes, int64_t B, int64_t ld, const int64_t* row_len,
+                                          const int64_t* seg_rows, const int64_t* seg_bounds, int64_t n_seg, int drop, void* d_out,
+                                          int64_t out_cap, int64_t* out_offsets, void* stream) {
+    if (!e && d_out) return fail(SVAD_EINVAL, "null engine");   // the sizing pass (d_out == NULL) is host-only and needs none
+    if ((elem_bytes != 2 && elem_bytes != 4) || B < 0 || n_seg < 0 || !out_offsets || (B > 0 && !row_len) || (n_seg > 0 && (!seg_rows || !seg_bounds)))
+        return fail(SVAD_EINVAL, "bad argument");
+    try {
+        std::vector<long long> plan;
+        int64_t k = 0, n_out = 0;
+        auto piece = [&](int64_t row, int64_t a, int64_t b) {   // wav[row][a:b] with Python's clamping of non-negative bounds
+            const int64_t len = row_len[row];
+            if (a > len) a = len;
+            if (b > len) b = len;
+            if (b > a) { plan.push_back(row * ld + a); plan.push_back(n_out); plan.push_back(b - a); n_out += b - a; }
+        };
+        for (int64_t row = 0; row < B; row++) {
+            out_offsets[row] = n_out;
+            if (row_len[row] < 0 || row_len[row] > ld) return fail(SVAD_EINVAL, "row_len out of range");
+            int64_t cur = 0;
+            for (; k < n_seg && seg_rows[k] == row; k++) {
+                const int64_t a = seg_bounds[2 * k], b = seg_bounds[2 * k + 1];
+                if (a < 0 || b < 0) return fail(SVAD_EINVAL, "negative segment bound");
+                if (drop) { piece(row, cur, a); cur = b; } else piece(row, a, b);
+            }
+            if (drop) piece(row, cur, row_len[row]);
+        }
+        if (k != n_seg) return fail(SVAD_EINVAL, "seg_rows must be sorted and < B");
+        out_offsets[B] = n_out;
+        if (!d_out || n_out == 0) return SVAD_OK;   // sizing pass
+        if (n_out > out_cap) return fail(SVAD_EINVAL, "output buffer too small: need %lld elements", (long long)n_out);
+        if (!d_wav) return fail(SVAD_EINVAL, "null audio");
+        CUDA_TRY(cudaSetDevice(e->device));
+        cudaStream_t st = (cudaStream_t)stream;
+        long long* d_plan = nullptr;
+        CUDA_TRY(cudaMallocAsync(&d_plan, plan.size() * sizeof(long long), st));
+        cudaError_t err = cudaMemcpyAsync(d_plan, plan.data(), plan.size() * sizeof(long long), cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) {
+            const long long npieces = (long long)(plan.size() / 3);
+            long long units = (n_out + kGatherUnit - 1) / kGatherUnit;
+            const int grid = (int)(units < (long long)e->sms * 8 ? units : (long long)e->sms * 8);
+            if (elem_bytes == 4) svad_gather_segments<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)d_wav, (uint32_t*)d_out, d_plan, npieces, n_out);
+            else svad_gather_segments<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)d_wav, (uint16_t*)d_out, d_plan, npieces, n_out);
+            err = cudaGetLastError();
+            e->launches++;
+        }
+        // the plan lives in pageable host memory: the copy above has been staged by the time cudaMemcpyAsync returns
+        cudaFreeAsync(d_plan, st);
+        if (err != cudaSuccess) return fail(SVAD_ECUDA, "collect_chunks: %s", cudaGetErrorString(err));
+        return SVAD_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(SVAD_ENOMEM, "out of memory");
+    }
 }

@@ -266,14 +266,16 @@ SVAD_HD float ld_sample(const int16_t* p) {
 #endif
 }
 
+// `dec` > 1: the row holds sr = dec * 16000 audio and only every dec-th sample is read -- the reference's `x[:, ::step]`
+// (utils_vad.py:39-42, 301-305) done by the load instead of a host-side slice; L counts the decimated samples.
 template <bool SR16, typename S>
-SVAD_HD float window_sample(const S* audio, long L, const float* ctx_in, long t, int i) {
+SVAD_HD float window_sample(const S* audio, long L, const float* ctx_in, long t, int i, int dec = 1) {
     using G = Geo<SR16>;
     if (i >= G::L1) i = 2 * G::L1 - 2 - i;           // xp[L1 + j] = x1[L1 - 2 - j]
     long a = t * G::n - G::ctx + i;
     if (a < 0) return ctx_in ? ctx_in[G::ctx + a] : 0.0f;
     if (a >= L) return 0.0f;
-    return ld_sample(audio + a);
+    return ld_sample(audio + a * dec);
 }
 
 // ---------------------------------------------------------------- STFT pass A
@@ -291,21 +293,21 @@ SVAD_HD int zitem_fr(int item) { return (item >> 3) & 1; }
 // Generic window fetch (context / reflect pad / zero tail resolved per sample): only the first and the last chunk of a
 // row take it, so it is kept out of line -- the fused kernel's steady-state loop has to fit the instruction cache.
 template <bool SR16, typename S>
-SVAD_COLD void stft_load_generic(int r, int fp, const S* audio, const float* ctx_in, long L, long t, float* xa, float* xb) {
+SVAD_COLD void stft_load_generic(int r, int fp, const S* audio, const float* ctx_in, long L, long t, float* xa, float* xb, int dec) {
     using G = Geo<SR16>;
 #pragma unroll 4
     for (int q = 0; q < G::NQ; q++) {
         const int m = r + 16 * q;
-        xa[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp) + m);
-        xb[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp + 1) + m);
+        xa[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp) + m, dec);
+        xb[q] = window_sample<SR16, S>(audio, L, ctx_in, t, G::hop * (2 * fp + 1) + m, dec);
     }
 }
 
-// `fast` (CTA-uniform): the whole padded window of chunk t lies inside the row, so the addresses are affine in
+// `fast` (CTA-uniform; never with dec > 1): the whole padded window of chunk t lies inside the row, so the addresses are affine in
 // (r, q) with the reflection resolved at compile time; otherwise the generic fetch handles context / zero tail.
 template <bool SR16, typename S>
 SVAD_HD void stft_load(int tid, int fp, const S* audio, const float* ctx_in, long L, long t, bool fast,
-                       float (&xa)[Geo<SR16>::NQ], float (&xb)[Geo<SR16>::NQ]) {
+                       float (&xa)[Geo<SR16>::NQ], float (&xb)[Geo<SR16>::NQ], int dec = 1) {
     using G = Geo<SR16>;
     const int r = tid & 15;
     if (!audio) {
@@ -327,7 +329,7 @@ SVAD_HD void stft_load(int tid, int fp, const S* audio, const float* ctx_in, lon
         }
     } else {
         float ta[G::NQ], tb[G::NQ];   // address-taken copies: xa / xb themselves stay in registers
-        stft_load_generic<SR16, S>(r, fp, audio, ctx_in, L, t, ta, tb);
+        stft_load_generic<SR16, S>(r, fp, audio, ctx_in, L, t, ta, tb, dec);
 #pragma unroll
         for (int q = 0; q < G::NQ; q++) { xa[q] = ta[q]; xb[q] = tb[q]; }
     }

@@ -32,14 +32,18 @@ inline bool read_container(const char* path, TensorMap& out, std::string& err) {
     FILE* f = fopen(path, "rb");
     if (!f) { err = std::string("cannot open ") + path; return false; }
     char magic[8]; uint32_t n = 0;
-    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "SVADW001", 8) || fread(&n, 4, 1, f) != 1) { fclose(f); err = "bad magic"; return false; }
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "SVADW001", 8) || fread(&n, 4, 1, f) != 1 || n > 4096) { fclose(f); err = "bad magic"; return false; }
     for (uint32_t i = 0; i < n; i++) {
         uint32_t nl = 0, nd = 0;
         if (fread(&nl, 4, 1, f) != 1 || nl > 255) { fclose(f); err = "bad name"; return false; }
         std::string name(nl, 0);
         if (fread(&name[0], 1, nl, f) != nl || fread(&nd, 4, 1, f) != 1 || nd > 4) { fclose(f); err = "bad tensor header"; return false; }
         HostTensor t; t.dims.resize(nd); size_t numel = 1;
-        for (uint32_t d = 0; d < nd; d++) { if (fread(&t.dims[d], 4, 1, f) != 1) { fclose(f); err = "bad dims"; return false; } numel *= t.dims[d]; }
+        for (uint32_t d = 0; d < nd; d++) {
+            if (fread(&t.dims[d], 4, 1, f) != 1) { fclose(f); err = "bad dims"; return false; }
+            numel *= t.dims[d];
+            if (numel > (size_t)1 << 26) { fclose(f); err = "tensor too large (corrupt container?)"; return false; }   // 64 Mi floats: 250x the largest real tensor
+        }
         t.data.resize(numel);
         if (fread(t.data.data(), 4, numel, f) != numel) { fclose(f); err = "truncated"; return false; }
         out[name] = std::move(t);

@@ -10,6 +10,8 @@
 // The native twin in the reference tree is examples/cpp/silero-vad-onnx.cpp:199-331.
 #include <cmath>
 #include <cstdint>
+#include <functional>
+#include <thread>
 #include <vector>
 
 #include "../../include/silero_vad_b200.h"
@@ -128,23 +130,49 @@ extern "C" void svad_segment_params_default(svad_segment_params* p) {
     p->use_max_poss_sil_at_max_speech = 1;
 }
 
+// Rows are independent streams: they are cut into contiguous ranges, one host thread per range (each thread keeps its
+// segments in a private vector), then the ranges are stitched in row order.  Threads: hardware concurrency, capped at 32
+// and at one per 64 rows (small batches stay single-threaded: thread start-up costs more than 64 automata).
 extern "C" int svad_speech_segments(const float* probs, int64_t B, int64_t T, int64_t ldp, const int64_t* audio_len,
                                     const svad_segment_params* p, int64_t* seg_offsets, int64_t* seg_bounds, int64_t cap,
                                     int64_t* n_total) {
     if (!p || (B > 0 && (!probs || !audio_len || !seg_offsets)) || B < 0 || T < 0 || ldp < T || !n_total) return SVAD_EINVAL;
     if (p->sampling_rate != 16000 && p->sampling_rate != 8000) return SVAD_EINVAL;
-    std::vector<Seg> segs;
+    const int64_t w = p->sampling_rate == 16000 ? 512 : 256;
+    int nthr = (int)std::thread::hardware_concurrency();
+    if (nthr < 1) nthr = 1;
+    if (nthr > 32) nthr = 32;
+    if ((int64_t)nthr > (B + 63) / 64) nthr = (int)((B + 63) / 64);
+    if (nthr < 1) nthr = 1;
+    struct Range { int64_t b0, b1; std::vector<Seg> segs; std::vector<int64_t> count; };
+    std::vector<Range> ranges((size_t)nthr);
+    auto work = [&](Range& r) {
+        std::vector<Seg> one;
+        r.count.assign((size_t)(r.b1 - r.b0), 0);
+        for (int64_t b = r.b0; b < r.b1; b++) {
+            // a stream shorter than T chunks only has ceil(len / w) meaningful probabilities
+            int64_t Tb = (audio_len[b] + w - 1) / w;
+            if (Tb > T) Tb = T;
+            r.count[(size_t)(b - r.b0)] = segments_one(probs + b * ldp, Tb, audio_len[b], *p, one);
+            r.segs.insert(r.segs.end(), one.begin(), one.end());
+        }
+    };
+    try {
+        for (int i = 0; i < nthr; i++) { ranges[(size_t)i].b0 = B * i / nthr; ranges[(size_t)i].b1 = B * (i + 1) / nthr; }
+        std::vector<std::thread> pool;
+        for (int i = 1; i < nthr; i++) pool.emplace_back(work, std::ref(ranges[(size_t)i]));
+        work(ranges[0]);
+        for (auto& t : pool) t.join();
+    } catch (...) {
+        return SVAD_ENOMEM;
+    }
     int64_t n = 0;
-    for (int64_t b = 0; b < B; b++) {
-        seg_offsets[b] = n;
-        // a stream shorter than T chunks only has ceil(len / w) meaningful probabilities
-        const int64_t w = p->sampling_rate == 16000 ? 512 : 256;
-        int64_t Tb = (audio_len[b] + w - 1) / w;
-        if (Tb > T) Tb = T;
-        segments_one(probs + b * ldp, Tb, audio_len[b], *p, segs);
-        for (const Seg& s : segs) {
-            if (seg_bounds && n < cap) { seg_bounds[2 * n] = s.start; seg_bounds[2 * n + 1] = s.end; }
-            n++;
+    for (const Range& r : ranges) {
+        size_t k = 0;
+        for (int64_t b = r.b0; b < r.b1; b++) {
+            seg_offsets[b] = n;
+            for (int64_t c = 0; c < r.count[(size_t)(b - r.b0)]; c++, k++, n++)
+                if (seg_bounds && n < cap) { seg_bounds[2 * n] = r.segs[k].start; seg_bounds[2 * n + 1] = r.segs[k].end; }
         }
     }
     if (B > 0) seg_offsets[B] = n;

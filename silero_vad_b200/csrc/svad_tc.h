@@ -135,8 +135,8 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
         for (long t = 0; t < a.T; t++) {
             SVAD_STAMP(0);
             // ---------------- STFT (CUDA cores) -> mag rows in tcgen05 atom layout
-            const bool fast = (t > 0) && ((t + 1) * G::n <= a.L);
-            if (t + 1 < a.T) {
+            const bool fast = (t > 0) && ((t + 1) * G::n <= a.L) && a.dec == 1;
+            if (t + 1 < a.T && a.dec == 1) {
                 constexpr int kPerLine = 128 / (int)sizeof(S), kLines = G::n / kPerLine;
                 for (int i = tc.tid; i < BT * kLines; i += kThreads) {
                     const int loc = i / kLines, line = i % kLines, g = g0 + loc;
@@ -144,12 +144,12 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     if (g < a.B && off < a.L) env.prefetch_l2(audio + (long)g * a.ld + off);
                 }
             }
-            if (t == 0) stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t, fast, xa, xb);
+            if (t == 0) stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t, fast, xa, xb, a.dec);
 #pragma unroll 1
             for (int rnd = 0; rnd < 4; rnd++) {
                 const int hs = rnd >> 1, fp = rnd & 1;
                 float na[G::NQ], nb[G::NQ];
-                if (rnd < 3) stft_load<SR16, S>(tc.tid, (rnd + 1) & 1, rnd >= 1 ? aud[1] : aud[0], rnd >= 1 ? cxp[1] : cxp[0], a.L, t, fast, na, nb);
+                if (rnd < 3) stft_load<SR16, S>(tc.tid, (rnd + 1) & 1, rnd >= 1 ? aud[1] : aud[0], rnd >= 1 ? cxp[1] : cxp[0], a.L, t, fast, na, nb, a.dec);
                 stft_pass_a<SR16, M>(tc, sm, xa, xb);
                 env.sync();
 #pragma unroll
@@ -499,7 +499,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                     a.probs[(long)g * a.ldp + t] = sigmoid_acc(a0 + a1);
                 }
             }
-            if (t + 1 < a.T) stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t + 1, ((t + 2) * G::n <= a.L), xa, xb);
+            if (t + 1 < a.T) stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t + 1, ((t + 2) * G::n <= a.L) && a.dec == 1, xa, xb, a.dec);
             SVAD_STAMP(10);
         }
         // ---- tile exit
@@ -521,7 +521,7 @@ SVAD_HD void run_cta_tc(Env& env, const TileArgs& a, int first_tile, int tile_st
                 const int loc = i / G::ctx, k = i % G::ctx, g = g0 + loc;
                 if (g < a.B) {
                     const float* cx = a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr;
-                    a.ctx_out[(long)g * G::ctx + k] = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k)
+                    a.ctx_out[(long)g * G::ctx + k] = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k, a.dec)
                                                                 : (cx ? cx[k] : 0.0f);
                 }
             }

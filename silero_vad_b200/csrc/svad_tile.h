@@ -18,7 +18,8 @@ namespace svad {
 
 struct TileArgs {
     const void* audio;      // [B][ld] samples (fp32 or int16 PCM, see run_cta's S), device (or host in the emulator)
-    long ld, L;             // row stride, valid samples per row (tail is zero-padded to T*n)
+    long ld, L;             // row stride (in stored samples), valid samples per row AFTER decimation (tail is zero-padded to T*n)
+    int dec;                // sample stride within a row: 1, or k for sr = k * 16000 input (utils_vad.py:39-42)
     int B;                  // streams
     long T;                 // chunk steps = ceil(L / n)
     const float* state_in;  // [2][B][128] or null (zeros)
@@ -103,9 +104,8 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
         for (long t = 0; t < a.T; t++) {
             // ---------------- STFT: 4 rounds (slot half hs, frame pair fp); the raw samples of round i+1 are
             // fetched into registers while round i is transformed, round 0 of the next step at the end of this one.
-            const bool fast = (t > 0) && ((t + 1) * G::n <= a.L);
-            if (t + 1 < a.T) {   // pull the next chunk of every stream of the tile into L2
-#pragma unroll
+            const bool fast = (t > 0) && ((t + 1) * G::n <= a.L) && a.dec == 1;
+            if (t + 1 < a.T && a.dec == 1) {   // pull the next chunk of every stream of the tile into L2
                 constexpr int kPerLine = 128 / (int)sizeof(S), kLines = G::n / kPerLine;
                 for (int i = tc.tid; i < BT * kLines; i += kThreads) {
                     const int loc = i / kLines, line = i % kLines, g = g0 + loc;
@@ -113,12 +113,12 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                     if (g < a.B && off < a.L) env.prefetch_l2(audio + (long)g * a.ld + off);
                 }
             }
-            if (t == 0) stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t, fast, xa, xb);
+            if (t == 0) stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t, fast, xa, xb, a.dec);
 #pragma unroll 1
             for (int rnd = 0; rnd < 4; rnd++) {
                 const int hs = rnd >> 1, fp = rnd & 1;
                 float na[G::NQ], nb[G::NQ];
-                if (rnd < 3) stft_load<SR16, S>(tc.tid, (rnd + 1) & 1, rnd >= 1 ? aud[1] : aud[0], rnd >= 1 ? cxp[1] : cxp[0], a.L, t, fast, na, nb);
+                if (rnd < 3) stft_load<SR16, S>(tc.tid, (rnd + 1) & 1, rnd >= 1 ? aud[1] : aud[0], rnd >= 1 ? cxp[1] : cxp[0], a.L, t, fast, na, nb, a.dec);
                 stft_pass_a<SR16>(tc, sm, xa, xb);
                 env.sync();
 #pragma unroll
@@ -180,7 +180,7 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                 if (slot_valid<RM>(tc.tid) && g < a.B) a.probs[(long)g * a.ldp + t] = head_prob(sm, tc.tid);
             }
             if (t + 1 < a.T)
-                stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t + 1, ((t + 2) * G::n <= a.L), xa, xb);
+                stft_load<SR16, S>(tc.tid, 0, aud[0], cxp[0], a.L, t + 1, ((t + 2) * G::n <= a.L) && a.dec == 1, xa, xb, a.dec);
         }
         // ---- tile exit: carry state / context out
         env.sync();
@@ -206,7 +206,7 @@ SVAD_HD void run_cta(Env& env, const TileArgs& a, int first_tile, int tile_strid
                 if (g < a.B) {
                     // new context = last ctx samples of the (zero-padded) final window
                     const float* cx = a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr;
-                    float v = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k)
+                    float v = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k, a.dec)
                                         : (cx ? cx[k] : 0.0f);
                     a.ctx_out[(long)g * G::ctx + k] = v;
                 }

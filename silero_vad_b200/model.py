@@ -40,21 +40,28 @@ class SileroVADB200:
         self._last_sr = 0
         self._last_batch_size = 0
 
-    def _validate_input(self, x, sr: int):
+    def _validate_input(self, x, sr: int, device_decimation=False):
+        """utils_vad.py:33-49.  With device_decimation the `x[:, ::step]` slice of sr = k * 16000 input is NOT taken here:
+        (x, 16000, step) is returned and the kernel reads every step-th sample itself."""
         if not torch.is_tensor(x):
             x = torch.as_tensor(x)
         if x.dim() == 1:
             x = x.unsqueeze(0)
         if x.dim() > 2:
             raise ValueError(f"Too many dimensions for input audio chunk {x.dim()}")
+        step = 1
         if sr != 16000 and (sr % 16000 == 0):
             step = sr // 16000
-            x = x[:, ::step]
+            if not device_decimation:
+                x = x[:, ::step]
             sr = 16000
         if sr not in self.sample_rates:
             raise ValueError(f"Supported sampling rates: {self.sample_rates} (or multiply of 16000)")
-        if sr / x.shape[1] > 31.25:
+        n_model = -(-x.shape[1] // step) if device_decimation else x.shape[1]
+        if n_model == 0 or sr / n_model > 31.25:
             raise ValueError("Input audio chunk is too short")
+        if device_decimation:
+            return x, sr, step
         return x, sr
 
     def _to_device(self, x, keep_pcm16=False):
@@ -65,10 +72,11 @@ class SileroVADB200:
         return x.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
 
     def __call__(self, x, sr: int):
-        x, sr = self._validate_input(x, sr)
+        x, sr, step = self._validate_input(x, sr, device_decimation=True)
         num_samples = 512 if sr == 16000 else 256
-        if x.shape[-1] != num_samples:
-            raise ValueError(f"Provided number of samples is {x.shape[-1]} (Supported values: 256 for 8000 sample rate, 512 for 16000)")
+        raw = x.shape[-1]
+        if -(-raw // step) != num_samples:
+            raise ValueError(f"Provided number of samples is {-(-raw // step)} (Supported values: 256 for 8000 sample rate, 512 for 16000)")
         batch_size = x.shape[0]
         context_size = 64 if sr == 16000 else 32
         if self._last_sr and self._last_sr != sr:
@@ -85,8 +93,8 @@ class SileroVADB200:
             out = torch.empty(batch_size, 1, device=self.device)
             st = torch.cuda.current_stream(self.device).cuda_stream
             # one chunk: state and context are read, advanced and written back in place by the kernel
-            self.engine.forward_device(sr, batch_size, num_samples, num_samples, _ptr(xd), _ptr(self._state), _ptr(self._context),
-                                       _ptr(self._state), _ptr(self._context), _ptr(out), 1, st)
+            self.engine.forward_device_ex(sr, batch_size, raw, xd.stride(0), _ptr(xd), 0, step, _ptr(self._state), _ptr(self._context),
+                                          _ptr(self._state), _ptr(self._context), _ptr(out), 1, st)
         self._last_sr = sr
         self._last_batch_size = batch_size
         return out if in_device == self.device else out.to(in_device)
@@ -103,13 +111,13 @@ class SileroVADB200:
         """Like audio_forward but leaves the probabilities on the GPU; with reset=False continues from the
         carried state/context (long streams fed in pieces whose length is a multiple of the chunk size).
         int16 tensors are taken as PCM and read by the kernel directly (half the bytes, same probabilities)."""
-        x, sr = self._validate_input(x, sr)
+        x, sr, step = self._validate_input(x, sr, device_decimation=True)
         if reset:
             self.reset_states()
         n = 512 if sr == 16000 else 256
         ctx = 64 if sr == 16000 else 32
-        B, L = x.shape
-        T = (L + n - 1) // n
+        B, L = x.shape                      # stored samples; the model sees every step-th one
+        T = (-(-L // step) + n - 1) // n
         if self._last_sr and self._last_sr != sr:
             self.reset_states()
         if self._last_batch_size and self._last_batch_size != B:
@@ -122,9 +130,8 @@ class SileroVADB200:
                 self._context = torch.zeros(B, ctx, device=self.device)
             probs = torch.empty(B, T, device=self.device)
             st = torch.cuda.current_stream(self.device).cuda_stream
-            fwd = self.engine.forward_device_pcm16 if xd.dtype == torch.int16 else self.engine.forward_device
-            fwd(sr, B, L, xd.stride(0), _ptr(xd), _ptr(self._state), _ptr(self._context), _ptr(self._state),
-                _ptr(self._context), _ptr(probs), max(T, 1), st)
+            self.engine.forward_device_ex(sr, B, L, xd.stride(0), _ptr(xd), 1 if xd.dtype == torch.int16 else 0, step, _ptr(self._state),
+                                          _ptr(self._context), _ptr(self._state), _ptr(self._context), _ptr(probs), max(T, 1), st)
         self._last_sr = sr
         self._last_batch_size = B
         return probs
@@ -135,7 +142,21 @@ class SileroVADB200:
                 self._last_sr, self._last_batch_size)
 
     def set_states(self, saved):
-        self._state, self._context, self._last_sr, self._last_batch_size = saved
+        """Resume streams parked with get_states().  The tensors are CLONED onto this model's device (the kernels advance
+        state and context in place, so the caller's snapshot must stay what it was and can be restored again) and their
+        shapes are checked against the recorded batch size / sample rate: they are handed to the kernel as raw pointers."""
+        state, context, last_sr, last_bs = saved
+        if (state is None) != (context is None):
+            raise ValueError("state and context must both be given or both be None")
+        if state is not None:
+            if last_sr not in (8000, 16000) or last_bs < 1:
+                raise ValueError("a saved state needs the sample rate and batch size it belongs to")
+            ctx = 64 if last_sr == 16000 else 32
+            if tuple(state.shape) != (2, last_bs, 128) or tuple(context.shape) != (last_bs, ctx):
+                raise ValueError(f"expected state [2, {last_bs}, 128] and context [{last_bs}, {ctx}], got {tuple(state.shape)} and {tuple(context.shape)}")
+            state = state.detach().to(device=self.device, dtype=torch.float32, copy=True).contiguous()
+            context = context.detach().to(device=self.device, dtype=torch.float32, copy=True).contiguous()
+        self._state, self._context, self._last_sr, self._last_batch_size = state, context, last_sr, last_bs
 
     def eval(self):
         return self

@@ -90,21 +90,29 @@ def get_speech_timestamps(audio: torch.Tensor,
             audio = audio.squeeze(0)
         if len(audio.shape) > 1:
             raise ValueError("More than one dimension in audio. Are you trying to process audio with 2 channels?")
+    fused = isinstance(model, SileroVADB200)
+    raw_audio, raw_rate = audio, sampling_rate
     if sampling_rate > 16000 and (sampling_rate % 16000 == 0):
         step = sampling_rate // 16000
         sampling_rate = 16000
-        audio = audio[::step]
+        if not fused:
+            audio = audio[::step]
         warnings.warn('Sampling rate is a multiply of 16000, casting to 16000 manually!')
     else:
         step = 1
     if sampling_rate not in [8000, 16000]:
         raise ValueError("Currently silero VAD models support 8000 and 16000 (or multiply of 16000) sample rates")
     window = 512 if sampling_rate == 16000 else 256
-    audio_length_samples = len(audio)
+    audio_length_samples = -(-len(raw_audio) // step) if fused else len(audio)    # = len(audio[::step])
 
     model.reset_states()
-    if isinstance(model, SileroVADB200) and audio_length_samples > 0:
-        probs = model.audio_forward(audio.unsqueeze(0), sampling_rate)[0].numpy()
+    if fused and audio_length_samples > 0:
+        # the kernel decimates (reads every step-th sample) and zero-pads the tail itself; a clip shorter than one window is
+        # padded up to it here, as the reference pads every chunk before the model call (utils_vad.py:323-327)
+        x = raw_audio
+        if audio_length_samples < window:
+            x = torch.nn.functional.pad(raw_audio, (0, window * step - len(raw_audio)))
+        probs = model.audio_forward(x.unsqueeze(0), raw_rate)[0].numpy()
         if progress_tracking_callback:
             for start in range(0, audio_length_samples, window):
                 progress_tracking_callback(min(start + window, audio_length_samples) / audio_length_samples * 100)
@@ -137,6 +145,9 @@ def get_speech_timestamps_batch(audio, model, lengths=None, sampling_rate: int =
         raise ValueError("audio must be [B, L]")
     B, L = audio.shape
     lengths = np.full(B, L, np.int64) if lengths is None else np.asarray(lengths, np.int64)
+    window = 512 if sampling_rate == 16000 else 256
+    if L < window:   # clips shorter than one window: padded like the reference pads every chunk (utils_vad.py:323-327)
+        audio = torch.nn.functional.pad(audio, (0, window - L))
     probs = model.audio_forward(audio, sampling_rate).numpy()
     p = _segment_params(sampling_rate, threshold, neg_threshold, min_speech_duration_ms, max_speech_duration_s,
                         min_silence_duration_ms, speech_pad_ms, min_silence_at_max_speech, use_max_poss_sil_at_max_speech)
@@ -257,25 +268,77 @@ class VADIteratorBatch:
         return out
 
 
-def collect_chunks(tss: List[dict], wav: torch.Tensor, seconds: bool = False, sampling_rate: int = None) -> torch.Tensor:
-    """Concatenate the audio inside the given segments (utils_vad.py:552-597)."""
+def _gather_chunks(tss_rows, wav2d, lengths, drop, model=None):
+    """One gather launch (svad_collect_chunks_device) over the segment table of B rows.  wav2d: [B, L] float32 or int16 (CPU
+    tensors are moved to the model's GPU).  Returns (flat device tensor, out_offsets[B+1])."""
+    eng_model = model if model is not None else _default_model(wav2d)
+    dev = eng_model.device
+    x = wav2d.to(device=dev).contiguous()
+    if x.dtype not in (torch.float32, torch.int16):
+        x = x.to(torch.float32)
+    B, L = x.shape
+    rows = np.asarray([b for b, tss in enumerate(tss_rows) for _ in tss], np.int64)
+    bounds = np.asarray([[int(d['start']), int(d['end'])] for tss in tss_rows for d in tss], np.int64).reshape(-1, 2)
+    lengths = np.full(B, L, np.int64) if lengths is None else np.asarray(lengths, np.int64)
+    eng = eng_model.engine
+    es = x.element_size()
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        offs = eng.collect_chunks_device(0, es, B, x.stride(0), lengths, rows, bounds, drop, 0, 0, st)   # sizing pass (host only)
+        out = torch.empty(int(offs[-1]), dtype=x.dtype, device=dev)
+        if out.numel():
+            eng.collect_chunks_device(x.data_ptr(), es, B, x.stride(0), lengths, rows, bounds, drop, out.data_ptr(), out.numel(), st)
+    return out, offs
+
+
+_models_by_device = {}
+
+
+def _default_model(t):
+    """Engine to run the gather on when the caller has none at hand: one per CUDA device, created on first use."""
+    idx = t.device.index if t.is_cuda else torch.cuda.current_device()
+    if idx not in _models_by_device:
+        _models_by_device[idx] = SileroVADB200(device=idx)
+    return _models_by_device[idx]
+
+
+def _chunks(tss, wav, seconds, sampling_rate, drop):
     if seconds and not sampling_rate:
         raise ValueError('sampling_rate must be provided when seconds is True')
     _tss = _seconds_to_samples_tss(tss, sampling_rate) if seconds else tss
-    return torch.cat([wav[i['start']:i['end']] for i in _tss])
+    if not drop and len(_tss) == 0:
+        return torch.cat([])                       # what the reference's torch.cat of an empty list does (raises)
+    if wav.dim() != 1 or any(d['start'] < 0 or d['end'] < 0 for d in _tss):
+        # negative (wrap-around) bounds or unusual shapes: plain slicing, nothing to accelerate
+        if drop:
+            chunks, cur = [], 0
+            for i in _tss:
+                chunks.append(wav[cur:i['start']])
+                cur = i['end']
+            chunks.append(wav[cur:])
+            return torch.cat(chunks)
+        return torch.cat([wav[i['start']:i['end']] for i in _tss])
+    out, _ = _gather_chunks([_tss], wav.unsqueeze(0), None, drop)
+    out = out.to(wav.dtype) if out.dtype != wav.dtype else out
+    return out if wav.is_cuda else out.to(wav.device)
+
+
+def collect_chunks(tss: List[dict], wav: torch.Tensor, seconds: bool = False, sampling_rate: int = None) -> torch.Tensor:
+    """Concatenate the audio inside the given segments (utils_vad.py:552-597): one gather launch over the segment table;
+    the result lives where `wav` lives (a CUDA `wav` never leaves the GPU)."""
+    return _chunks(tss, wav, seconds, sampling_rate, drop=False)
 
 
 def drop_chunks(tss: List[dict], wav: torch.Tensor, seconds: bool = False, sampling_rate: int = None) -> torch.Tensor:
-    """Concatenate the audio outside the given segments (utils_vad.py:600-646)."""
-    if seconds and not sampling_rate:
-        raise ValueError('sampling_rate must be provided when seconds is True')
-    _tss = _seconds_to_samples_tss(tss, sampling_rate) if seconds else tss
-    chunks, cur = [], 0
-    for i in _tss:
-        chunks.append(wav[cur:i['start']])
-        cur = i['end']
-    chunks.append(wav[cur:])
-    return torch.cat(chunks)
+    """Concatenate the audio outside the given segments (utils_vad.py:600-646), same mechanism."""
+    return _chunks(tss, wav, seconds, sampling_rate, drop=True)
+
+
+def collect_chunks_batch(tss_rows, wav: torch.Tensor, lengths=None, drop: bool = False, model=None):
+    """B rows at once: tss_rows[b] = segment list of row b of wav[B, L] (float32 or int16 PCM).  Returns the list of B
+    per-row results as views of ONE device buffer filled by ONE gather launch."""
+    out, offs = _gather_chunks(tss_rows, wav, lengths, drop, model)
+    return [out[int(offs[b]):int(offs[b + 1])] for b in range(len(tss_rows))]
 
 
 def _seconds_to_samples_tss(tss: List[dict], sampling_rate: int) -> List[dict]:
@@ -332,7 +395,7 @@ def init_jit_model(model_path: str = None, device=None):
     if isinstance(device, torch.device):
         if device.type != "cuda":
             raise RuntimeError("silero_vad_b200 runs on a CUDA device only (no CPU fallback)")
-        device = device.index or 0
+        device = torch.cuda.current_device() if device.index is None else device.index
     return SileroVADB200(device=device)
 
 

@@ -227,7 +227,7 @@ extern "C" int svad_emu_forward_tc(const char* weights, int sr, int rm, int B, l
     if (!(sr16 ? pack_branch_tc<true>(tm, pb, err) : pack_branch_tc<false>(tm, pb, err))) return -2;
     const int n = sr16 ? 512 : 256;
     TileArgs a{};
-    a.audio = audio; a.ld = L; a.L = L; a.B = B; a.T = (L + n - 1) / n;
+    a.audio = audio; a.ld = L; a.L = L; a.dec = 1; a.B = B; a.T = (L + n - 1) / n;
     a.state_in = state_in; a.ctx_in = ctx_in; a.ctx_ld = sr16 ? 64 : 32; a.state_out = state_out; a.ctx_out = ctx_out;
     a.probs = probs; a.ldp = a.T; a.tape = pb.tape.data(); a.consts = pb.consts.data();
     const int bt = 4 * rm, ntiles = (B + bt - 1) / bt;
@@ -249,7 +249,7 @@ extern "C" int svad_emu_forward(const char* weights, int sr, int rm, int B, long
     if (!(sr16 ? pack_branch<true>(tm, pb, err) : pack_branch<false>(tm, pb, err))) return -2;
     const int n = sr16 ? 512 : 256;
     TileArgs a{};
-    a.audio = audio; a.ld = L; a.L = L; a.B = B; a.T = (L + n - 1) / n;
+    a.audio = audio; a.ld = L; a.L = L; a.dec = 1; a.B = B; a.T = (L + n - 1) / n;
     a.state_in = state_in; a.ctx_in = ctx_in; a.ctx_ld = sr16 ? 64 : 32; a.state_out = state_out; a.ctx_out = ctx_out;
     a.probs = probs; a.ldp = a.T; a.tape = pb.tape.data(); a.consts = pb.consts.data();
     const int bt = 4 * rm, ntiles = (B + bt - 1) / bt;

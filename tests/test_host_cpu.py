@@ -285,3 +285,82 @@ def test_reference_model_constructors_exist():
     assert list(inspect.signature(U.OnnxWrapper.__init__).parameters) == ["self", "path", "force_onnx_cpu"]
     with pytest.raises(RuntimeError, match="CUDA device only"):
         U.init_jit_model("silero_vad.jit", torch.device("cpu"))
+
+
+def test_segments_threaded_batch_equals_per_row():
+    """svad_speech_segments cuts large batches into row ranges, one host thread each: same lists as one row at a time."""
+    from silero_vad_b200 import _cabi
+    rng = np.random.default_rng(11)
+    B, T = 700, 90
+    probs = rng.uniform(0, 1, (B, T)).astype(np.float32)
+    probs[rng.uniform(size=(B, T)) < 0.5] *= 0.2
+    lens = rng.integers(1, T * 512 + 1, B).astype(np.int64)
+    p = _params({}, 16000)
+    whole = _cabi.speech_segments(probs, lens, p)
+    for b in range(0, B, 37):
+        assert _cabi.speech_segments(probs[b:b + 1], lens[b:b + 1], p)[0] == whole[b], b
+
+
+def test_collect_chunks_plan_sizes_like_python_slices():
+    """Sizing pass of svad_collect_chunks_device (host only, no engine): per-row output lengths equal what torch slicing gives."""
+    import ctypes
+    from silero_vad_b200 import _cabi
+    L = _cabi.lib()
+    rng = np.random.default_rng(3)
+    B, ld = 5, 1000
+    row_len = np.asarray([1000, 0, 700, 1000, 10], np.int64)
+    rows, bounds = [], []
+    for b in range(B):
+        for _ in range(int(rng.integers(0, 6))):
+            a, e = sorted(rng.integers(0, 1300, 2).tolist())
+            rows.append(b); bounds.append([a, e])
+    rows, bounds = np.asarray(rows, np.int64), np.asarray(bounds, np.int64).reshape(-1, 2)
+    for drop in (0, 1):
+        offs = np.zeros(B + 1, np.int64)
+        rc = L.svad_collect_chunks_device(None, None, 4, B, ld, row_len.ctypes.data, rows.ctypes.data, bounds.ctypes.data, len(rows), drop,
+                                          None, 0, offs.ctypes.data, None)
+        assert rc == 0, L.svad_last_error()
+        for b in range(B):
+            w = np.arange(row_len[b])
+            tab = bounds[rows == b]
+            if drop:
+                parts, cur = [], 0
+                for a, e in tab:
+                    parts.append(w[cur:a]); cur = e
+                parts.append(w[cur:])
+                want = sum(len(x) for x in parts)
+            else:
+                want = sum(len(w[a:e]) for a, e in tab)
+            assert offs[b + 1] - offs[b] == want, (drop, b)
+    bad = np.asarray([[-1, 5]], np.int64)
+    offs = np.zeros(2, np.int64)
+    assert L.svad_collect_chunks_device(None, None, 4, 1, ld, row_len.ctypes.data, np.zeros(1, np.int64).ctypes.data, bad.ctypes.data, 1, 0,
+                                        None, 0, offs.ctypes.data, None) == -1
+
+
+def test_corrupt_weight_container_is_an_error_not_a_crash(tmp_path):
+    """svad_engine_create: malformed containers return SVAD_EWEIGHTS (no exception across the C boundary, no huge allocation)."""
+    import ctypes
+    import struct
+    from silero_vad_b200 import _cabi
+    from silero_vad_b200.model import WEIGHTS
+    L = _cabi.lib()
+    good = WEIGHTS.read_bytes()
+    cases = {"trunc": good[: len(good) // 2], "magic": b"XXXXXXXX" + good[8:],
+             "hugedim": good[:12] + struct.pack("<I", 5) + b"hello" + struct.pack("<I", 2) + struct.pack("<II", 0x7fffffff, 0x7fffffff),
+             "count": good[:8] + struct.pack("<I", 0xffffffff) + good[12:]}
+    for name, blob in cases.items():
+        f = tmp_path / f"{name}.weights"
+        f.write_bytes(blob)
+        h = ctypes.c_void_p()
+        rc = L.svad_engine_create(str(f).encode(), 0, ctypes.byref(h))
+        assert rc == -2 and not h.value, (name, rc, L.svad_last_error())
+    h = ctypes.c_void_p()
+    assert L.svad_engine_create(str(tmp_path / "missing").encode(), 0, ctypes.byref(h)) == -2
+
+
+def test_build_hash_tracks_sources():
+    """_cabi.lib() rebuilds when the sources change: the staleness check is a content hash, not file times."""
+    from silero_vad_b200 import build as B
+    assert not B.stale()
+    assert B.HASH.read_text().strip() == B.source_hash()

@@ -95,3 +95,40 @@ def test_variants_and_iterator(oracle, fixtures, meta):
     assert ev == meta["test16k"]["vad_iterator_events_seconds"]
     pr = oracle.audio_forward(fx["audio"][:200_123], 16000)[0].tolist()
     assert seg(O.get_speech_timestamps(pr, 200_123)) == v["ragged_tail"]
+
+
+@pytest.mark.parametrize("sr", [16000, 8000])
+def test_r2_structured_signal(oracle, synthetic, sr):
+    """Reference harness examples/openvino/verify.py:31-51,157-182: the structured 22 s synthetic signal, chained state,
+    max-abs below tolerance AND identical segmentation under the harness's thresholder (verify.py:116-127)."""
+    import hashlib
+    import json
+    from recipes import r2_segments, synthetic_r2
+    meta = json.loads((O._REPO / "tests/golden/round2.json").read_text())[f"r2_{sr}"]
+    audio = synthetic_r2(sr)
+    assert hashlib.md5(audio.tobytes()).hexdigest() == meta["audio_md5"]
+    p = oracle.audio_forward(audio, sr)[0]
+    assert p.shape == synthetic[f"r2_{sr}_probs"].shape
+    assert np.abs(p - synthetic[f"r2_{sr}_probs"]).max() < TOL
+    assert [list(s) for s in r2_segments(p)] == meta["segments"]
+    assert [list(s) for s in r2_segments(p, thr=0.05, min_chunks=2)] == meta["segments_thr005_min2"]
+
+
+@pytest.mark.parametrize("sr", [16000, 8000])
+def test_bench_workload_rows(oracle, sr):
+    """The 64 rows of bench.py's workload (R1 noise, 64 chunks) that the GPU test checks: oracle vs the reference model."""
+    import json
+    from recipes import r1_audio
+    rows = json.loads((O._REPO / "tests/golden/round2.json").read_text())["bench_rows"]
+    gold = np.load(O._REPO / "tests/golden/round2.npz")[f"bench_{sr}_probs"]
+    n = 512 if sr == 16000 else 256
+    x = np.stack([r1_audio(sr, b, n * 64) for b in rows])
+    assert np.abs(oracle.audio_forward(x, sr, nthreads=8) - gold).max() < TOL
+
+
+@pytest.mark.parametrize("sr", [32000, 48000])
+def test_decimated_rates(oracle, sr):
+    """sr = k * 16000 (utils_vad.py:39-42): the oracle on audio[::k] against the reference called with the full-rate audio."""
+    z = np.load(O._REPO / "tests/golden/round2.npz")
+    p = oracle.audio_forward(z[f"decim_{sr}_audio"][:: sr // 16000].copy(), 16000)
+    assert np.abs(p - z[f"decim_{sr}_probs"]).max() < TOL
