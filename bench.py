@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--chunks", type=int, default=64, help="chunks per stream per step")
     ap.add_argument("--sr", type=int, default=16000, choices=[16000, 8000])
-    ap.add_argument("--kernel", default="tc", choices=["tc", "fp32"], help="tc: tcgen05 split-TF32 for every dense layer (default); fp32: all CUDA cores")
+    ap.add_argument("--kernel", default="tc", choices=["h16", "tc", "fp32"], help="h16: tcgen05 split-fp16 two-loop kernel; tc: tcgen05 split-TF32; fp32: all CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

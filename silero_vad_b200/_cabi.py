@@ -100,8 +100,8 @@ class Engine:
         return lib().svad_engine_launch_count(self._h)
 
     def set_kernel(self, kernel):
-        """0 / 'fp32' = CUDA-core kernel, 1 / 'tc' = tcgen05 split-TF32 kernel."""
-        check(lib().svad_engine_set_kernel(self._h, {"fp32": 0, "tc": 1}.get(kernel, kernel)))
+        """0 / 'fp32' = CUDA-core kernel, 1 / 'tc' = tcgen05 split-TF32 kernel, 2 / 'h16' = tcgen05 split-fp16 two-loop kernel."""
+        check(lib().svad_engine_set_kernel(self._h, {"fp32": 0, "tc": 1, "h16": 2}.get(kernel, kernel)))
 
     def set_small_batch_max(self, streams):
         check(lib().svad_engine_set_small_batch_max(self._h, streams))

@@ -11,7 +11,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB = PKG / "lib" / "libsilero_vad_b200.so"
 SOURCES = [PKG / "csrc" / "svad_api.cu", PKG / "csrc" / "svad_segments.cpp"]
-HEADERS = sorted((PKG / "csrc").glob("*.h")) + [PKG.parent / "include" / "silero_vad_b200.h"]
+HEADERS = sorted((PKG / "csrc").glob("*.h")) + sorted((PKG / "csrc").glob("*.cuh")) + [PKG.parent / "include" / "silero_vad_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xptxas", "-v"]
 HASH = PKG / "lib" / "source_hash.txt"
@@ -39,8 +39,24 @@ def stale():
     return not (LIB.exists() and HASH.exists() and HASH.read_text().strip() == source_hash())
 
 
+def build_debug():
+    """Second library with -DSVAD_H16_DEBUG (the fp16 kernel dumps every activation of CTA 0's first two steps): only the
+    bring-up tools load it (SVAD_DEBUG_LIB=1)."""
+    dbg = LIB.with_name("libsilero_vad_b200_dbg.so")
+    r = subprocess.run([nvcc_path(), *NVCC_FLAGS, "-DSVAD_H16_DEBUG", "-o", str(dbg), *map(str, SOURCES)], capture_output=True, text=True)
+    if r.returncode:
+        print(r.stdout, r.stderr)
+        raise RuntimeError("nvcc failed building %s" % dbg)
+    return dbg
+
+
 def build(force=False, verbose=False):
-    """Compile if missing or older than its sources. Returns the library path."""
+    """Compile if missing or built from other sources. Returns the library path."""
+    if os.environ.get("SVAD_DEBUG_LIB") == "1":
+        dbg = LIB.with_name("libsilero_vad_b200_dbg.so")
+        if not dbg.exists():
+            raise RuntimeError("debug library missing: run silero_vad_b200.build.build_debug() first")
+        return dbg
     if force or stale():
         LIB.parent.mkdir(exist_ok=True)
         cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]

@@ -21,6 +21,7 @@
 #include "../../include/silero_vad_b200.h"
 #include "svad_tc.h"
 #include "svad_small.h"
+#include "svad_h16.cuh"
 
 using namespace svad;
 
@@ -599,9 +600,12 @@ struct svad_engine {
     float* d_consts[2] = {nullptr, nullptr};
     float* d_tape_tc[2] = {nullptr, nullptr};  // tensor-core kernel
     float* d_consts_tc[2] = {nullptr, nullptr};
+    unsigned char* d_h16_f[2] = {nullptr, nullptr};   // fp16 split kernel: front / back weight tapes, constants
+    unsigned char* d_h16_b[2] = {nullptr, nullptr};
+    float* d_h16_c[2] = {nullptr, nullptr};
     float* d_small[2] = {nullptr, nullptr};    // small-batch cluster kernel: 8 per-CTA weight slices
     int small_max = 256;                       // streams up to which the cluster kernel is used (0 = never); crossover with the tile kernels measured at ~256
-    int kernel = 1;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32 (default)
+    int kernel = 1;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32, 2 = tcgen05 split-fp16 two-loop kernel
     long long* dbg = nullptr;
     int64_t launches = 0;
     // staging for the host-buffer entry points
@@ -666,6 +670,17 @@ static int engine_upload(svad_engine* e, int device, int sms, const TensorMap& t
         CUDA_TRY(cudaMalloc(&e->d_consts_tc[b], pbt[b].consts.size() * 4));
         CUDA_TRY(cudaMemcpy(e->d_tape_tc[b], pbt[b].tape.data(), pbt[b].tape.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(e->d_consts_tc[b], pbt[b].consts.data(), pbt[b].consts.size() * 4, cudaMemcpyHostToDevice));
+        {
+            PackedH16 ph;
+            std::string err;
+            if (!(b == 0 ? pack_branch_h16<true>(tm, ph, err) : pack_branch_h16<false>(tm, ph, err))) return fail(SVAD_EWEIGHTS, "%s", err.c_str());
+            CUDA_TRY(cudaMalloc(&e->d_h16_f[b], ph.tapeF.size()));
+            CUDA_TRY(cudaMalloc(&e->d_h16_b[b], ph.tapeB.size()));
+            CUDA_TRY(cudaMalloc(&e->d_h16_c[b], ph.consts.size() * 4));
+            CUDA_TRY(cudaMemcpy(e->d_h16_f[b], ph.tapeF.data(), ph.tapeF.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(e->d_h16_b[b], ph.tapeB.data(), ph.tapeB.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(e->d_h16_c[b], ph.consts.data(), ph.consts.size() * 4, cudaMemcpyHostToDevice));
+        }
         std::vector<float> blobs;
         if (b == 0) pack_small<true>(tm, blobs); else pack_small<false>(tm, blobs);
         CUDA_TRY(cudaMalloc(&e->d_small[b], blobs.size() * 4));
@@ -680,7 +695,8 @@ static int engine_upload(svad_engine* e, int device, int sms, const TensorMap& t
 extern "C" void svad_engine_destroy(svad_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    for (int b = 0; b < 2; b++) { cudaFree(e->d_tape[b]); cudaFree(e->d_consts[b]); cudaFree(e->d_tape_tc[b]); cudaFree(e->d_consts_tc[b]); cudaFree(e->d_small[b]); }
+    for (int b = 0; b < 2; b++) { cudaFree(e->d_tape[b]); cudaFree(e->d_consts[b]); cudaFree(e->d_tape_tc[b]); cudaFree(e->d_consts_tc[b]); cudaFree(e->d_small[b]);
+                                  cudaFree(e->d_h16_f[b]); cudaFree(e->d_h16_b[b]); cudaFree(e->d_h16_c[b]); }
     if (e->h_pin) cudaFreeHost(e->h_pin);
     if (e->d_buf) cudaFree(e->d_buf);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -695,7 +711,7 @@ extern "C" int svad_engine_set_tile_rows(svad_engine* e, int rows) {
     return SVAD_OK;
 }
 extern "C" int svad_engine_set_kernel(svad_engine* e, int kernel) {
-    if (!e || (kernel != 0 && kernel != 1)) return fail(SVAD_EINVAL, "kernel must be 0 (fp32 CUDA cores) or 1 (tcgen05 split-TF32)");
+    if (!e || kernel < 0 || kernel > 2) return fail(SVAD_EINVAL, "kernel must be 0 (fp32 CUDA cores), 1 (tcgen05 split-TF32) or 2 (tcgen05 split-fp16, two-loop)");
     e->kernel = kernel;
     return SVAD_OK;
 }
@@ -768,6 +784,33 @@ static int launch_small(svad_engine* e, const TileArgs& a, cudaStream_t st) {
     return SVAD_OK;
 }
 
+// fp16 split kernel: streams per tile chosen so that the tiles fill whole waves of SMs (B = 4096 on 148 SMs: 147 tiles of 28).
+static int pick_bt(const svad_engine* e, int B) {
+    if (e->tile_rows) return 4 * e->tile_rows;
+    const long tiles32 = (B + 31) / 32, waves = (tiles32 + e->sms - 1) / e->sms;
+    const long target = waves * e->sms;
+    long bt = (B + target - 1) / target;
+    return (int)(bt < 1 ? 1 : (bt > 32 ? 32 : bt));
+}
+
+template <bool SR16, typename S>
+static int launch_h16(svad_engine* e, const TileArgs& a, cudaStream_t st) {
+    auto kern = svad_fused_h16<SR16, S>;
+    static bool configured[16] = {};
+    if (!configured[e->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H16Map::total));
+        configured[e->device & 15] = true;
+    }
+    const int bt = pick_bt(e, a.B);
+    const int ntiles = (a.B + bt - 1) / bt;
+    const int grid = ntiles < e->sms ? ntiles : e->sms;
+    const int br = SR16 ? 0 : 1;
+    kern<<<grid, kH16Threads, H16Map::total, st>>>(a, e->d_h16_f[br], e->d_h16_b[br], ntiles, bt);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return SVAD_OK;
+}
+
 // rows per thread that minimises (waves x rows): the FFMA work of a CTA step is proportional to RM.
 static int pick_rows(const svad_engine* e, int B) {
     if (e->tile_rows) return e->tile_rows;
@@ -785,6 +828,7 @@ static int pick_rows(const svad_engine* e, int B) {
 template <bool SR16, typename S>
 static int launch_rm(svad_engine* e, const TileArgs& a, cudaStream_t st) {
     if (a.B <= e->small_max) return launch_small<SR16, S>(e, a, st);
+    if (e->kernel == 2) return launch_h16<SR16, S>(e, a, st);
     if (e->kernel == 1) {   // tensor-core kernel: MMA cost does not depend on the tile rows; only 7 and 8 are built
         if (a.T > 4000000) return fail(SVAD_EINVAL, "tensor-core kernel: at most 4e6 chunks per call (feed long streams in pieces)");
         const int rm = e->tile_rows ? e->tile_rows : pick_rows(e, a.B);
@@ -822,7 +866,7 @@ static int forward_impl(svad_engine* e, int sr, int B, int64_t Lraw, int64_t ld,
     a.state_out = d_state_out; a.ctx_out = d_ctx_out;
     a.probs = d_probs; a.ldp = ldp; a.dbg = e->dbg;
     a.tape = e->kernel == 1 ? e->d_tape_tc[br] : e->d_tape[br];
-    a.consts = e->kernel == 1 ? e->d_consts_tc[br] : e->d_consts[br];
+    a.consts = e->kernel == 2 && B > e->small_max ? e->d_h16_c[br] : (e->kernel == 1 ? e->d_consts_tc[br] : e->d_consts[br]);
     if (fmt == kI16) return sr == 16000 ? launch_rm<true, int16_t>(e, a, st) : launch_rm<false, int16_t>(e, a, st);
     return sr == 16000 ? launch_rm<true, float>(e, a, st) : launch_rm<false, float>(e, a, st);
 }

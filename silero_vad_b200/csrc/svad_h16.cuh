@@ -1,0 +1,817 @@
+// svad_h16.cuh -- `svad_fused_h16`: the whole per-chunk forward pass on tcgen05 with fp16 split-precision operands, as
+// TWO software-pipelined loops per CTA that overlap the CUDA-core and the tensor-core work of consecutive chunk steps.
+//
+// One persistent CTA per SM owns a tile of up to 32 streams (N of every MMA) and walks it through all T chunks with
+// (h, c) and the audio context resident on the SM.  Per chunk step:
+//
+//   FRONT loop (step t+1)                                      BACK loop (step t)
+//   EF  stage window  -> xp (fp16 hi | lo, [sample][slot])
+//   MF  STFT = basis . xp            (tcgen05, N = 128)
+//   EF  |re, im| -> mag (hi | lo)                               EB  enc1 accumulators -> e1      <- hand-over F -> B
+//   MF  enc0 (3 taps x Kt bins)      (N = 96 / 128)             MB  enc2        EB -> e2
+//   EF  + bias + Nyquist bin, ReLU -> e0                        MB  enc3        EB -> e3
+//   MF  enc1 (stride 2)              (M = 64)   ----------->    MB  LSTM gates = W . [e3 ; h]    (4 x M = 128, N = 64 | 32)
+//                                                               EB  gate math, c, h' -> h ; head -> probability
+//
+// The front half of step t+1 depends only on the audio, so it runs while the back half of step t (which carries the
+// recurrence) is still in flight: the tensor pipe works on one loop's MMAs while the CUDA cores run the other loop's
+// epilogue.  Roles are fixed per warp (EF = warps 0-3, EB = warps 4-7: one warp per TMEM lane quarter each; MF / MB = one
+// thread each issuing tcgen05.mma; RF / RB = one thread each streaming the loop's weight tape L2 -> shared memory with
+// cp.async.bulk through its own ring).  All hand-overs are mbarriers that complete exactly once per step.
+//
+// Shared memory (H16Map): every layer's output overwrites its input -- the MMAs reading the input have completed into TMEM
+// before the epilogue writes -- so one 80 KB region serves xp -> mag -> e0 and one 16 KB region e1 -> e2 -> e3.  Activation
+// buffers are the B operands as they sit: rows of 32 slots x fp16 = 64 B per channel, MN-major SWIZZLE_64B atoms (8 rows,
+// 16-byte chunk ^= (row >> 1) & 3); frames / hi | lo blocks are further N atoms at the descriptor's LBO stride.
+// TMEM (512 columns): front [0,256): STFT tiles -> enc0 [0,128), enc1 [192,256); back [256,512): enc2 [256,288),
+// enc3 [288,320), then the four LSTM gate blocks of 64 columns (w_hi . [x_hi | x_lo] is ONE N = 64 instruction).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "svad_h16_pack.h"
+#include "svad_tile.h"
+
+namespace svad {
+namespace h16 {
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---------------------------------------------------------------- mbarriers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Waits until the phase with this parity has completed.  The spin is bounded: a protocol error traps (the launch fails loudly)
+// instead of hanging the GPU.
+// Between polls the thread sleeps ~32 ns: twelve warps share four schedulers, and a waiter that polls flat out takes issue
+// slots (and the pipe SYNCS runs on) from the warps doing the epilogue math -- measured: 58 % of all executed instructions were
+// spin-loop instructions and every phase ran 3x slower than alone.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        __nanosleep(32);
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done) mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // one epilogue group
+
+// ---------------------------------------------------------------- descriptors / MMA issue (one thread)
+__device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ uint64_t desc_a(uint32_t saddr) { return desc(saddr, 16, 1024, 2); }              // K-major SWIZZLE_128B weight tile
+__device__ __forceinline__ uint64_t desc_b(uint32_t saddr, uint32_t lbo) { return desc(saddr, lbo, 512, 4); }   // MN-major SWIZZLE_64B activation rows
+// D fp32, A / B fp16, A K-major, B MN-major
+__device__ __forceinline__ constexpr uint32_t idesc(int M, int N) { return (1u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+// The four K = 16 steps of one 64-wide K chunk, NP (A, B) descriptor pairs per step, all into accumulator `d`.  One asm block:
+// the descriptors advance in registers (A by 32 B, B by 16 rows = 1024 B per step) -- issuing instruction by instruction from
+// C++ costs ~300 cycles each (tools/umma_f16_unit.cu), far above the 41-65 cycles the tensor pipe needs.
+// Pair 0 uses instruction descriptor i0, pairs 1 and 2 use i12 (the LSTM's w_lo . x_hi has another N).
+#define SVAD_H16_STEP(N) "add.s64 a0, %1, " #N "*2; add.s64 b0, %2, " #N "*64; add.s64 a1, %3, " #N "*2; add.s64 b1, %4, " #N "*64; add.s64 a2, %5, " #N "*2; add.s64 b2, %6, " #N "*64;\n"
+#define SVAD_H16_M0(P) "tcgen05.mma.cta_group::1.kind::f16 [%0], a0, b0, %7, " P ";\n"
+#define SVAD_H16_M1 "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %9, t;\n"
+#define SVAD_H16_M2 "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %9, t;\n"
+template <int NP>
+__device__ __forceinline__ void mma_chunk(uint32_t d, uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1, uint64_t a2, uint64_t b2, uint32_t i0, uint32_t i12,
+                                          bool acc_first) {
+    const uint32_t accf = acc_first ? 1u : 0u;
+    if constexpr (NP == 3) {
+        asm volatile("{\n.reg .pred p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
+                     SVAD_H16_STEP(0) SVAD_H16_M0("p") SVAD_H16_M1 SVAD_H16_M2 SVAD_H16_STEP(1) SVAD_H16_M0("t") SVAD_H16_M1 SVAD_H16_M2
+                     SVAD_H16_STEP(2) SVAD_H16_M0("t") SVAD_H16_M1 SVAD_H16_M2 SVAD_H16_STEP(3) SVAD_H16_M0("t") SVAD_H16_M1 SVAD_H16_M2 "}\n"
+                     ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(i0), "r"(accf), "r"(i12) : "memory");
+    } else if constexpr (NP == 2) {
+        asm volatile("{\n.reg .pred p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
+                     SVAD_H16_STEP(0) SVAD_H16_M0("p") SVAD_H16_M1 SVAD_H16_STEP(1) SVAD_H16_M0("t") SVAD_H16_M1
+                     SVAD_H16_STEP(2) SVAD_H16_M0("t") SVAD_H16_M1 SVAD_H16_STEP(3) SVAD_H16_M0("t") SVAD_H16_M1 "}\n"
+                     ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(i0), "r"(accf), "r"(i12) : "memory");
+    } else {
+        asm volatile("{\n.reg .pred p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
+                     SVAD_H16_STEP(0) SVAD_H16_M0("p") SVAD_H16_STEP(1) SVAD_H16_M0("t") SVAD_H16_STEP(2) SVAD_H16_M0("t") SVAD_H16_STEP(3) SVAD_H16_M0("t") "}\n"
+                     ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(i0), "r"(accf), "r"(i12) : "memory");
+    }
+}
+#undef SVAD_H16_STEP
+#undef SVAD_H16_M0
+#undef SVAD_H16_M1
+#undef SVAD_H16_M2
+
+// ---------------------------------------------------------------- TMEM loads, fp16 split stores
+// 16 consecutive accumulator columns of this thread's TMEM lane.  The load is asynchronous: several are issued back to back and
+// tmem_wait() is called once before the first use (a TMEM round trip costs hundreds of cycles while the other loop's MMAs run).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+                   "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float sqrt_fast(float v) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }   // rel. error 2^-23
+// (hi, lo) halves of two scaled values packed as {v0, v1}; saturating conversions
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    uint32_t h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v0));
+    const __half2 hh = *reinterpret_cast<const __half2*>(&h);
+    const float2 hf = __half22float2(hh);
+    uint32_t l;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(v1 - hf.y), "f"(v0 - hf.x));
+    hi = h; lo = l;
+}
+// 16 consecutive slots [16*half, +16) of activation row `row` (already scaled) -> the row's hi and lo images (row pitch 64 B)
+__device__ __forceinline__ void store_row16(unsigned char* hi_base, unsigned char* lo_base, int row, int half, const float (&v)[16]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    const int sw = (row >> 1) & 3;
+    const int c0 = ((2 * half) ^ sw) * 16, c1 = ((2 * half + 1) ^ sw) * 16;
+    *reinterpret_cast<uint4*>(hi_base + row * 64 + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(hi_base + row * 64 + c1) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4*>(lo_base + row * 64 + c0) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(lo_base + row * 64 + c1) = make_uint4(l[4], l[5], l[6], l[7]);
+}
+__device__ __forceinline__ float relu_f(float v) { return v > 0.0f ? v : 0.0f; }
+
+// Debug dump (svad_engine_set_debug_buffer): CTA 0 writes the fp32 value of every activation of its steps 0 and 1 before the
+// fp16 split, [step][region][row][slot]; tools/h16_check.py compares them with the CPU model of tools/h16_numerics.py.
+constexpr int kDumpMag = 0, kDumpNyq = kDumpMag + 4 * 128 * 32, kDumpE0 = kDumpNyq + 128, kDumpE1 = kDumpE0 + 4 * 128 * 32, kDumpE2 = kDumpE1 + 2 * 64 * 32,
+              kDumpE3 = kDumpE2 + 64 * 32, kDumpGates = kDumpE3 + 128 * 32, kDumpH = kDumpGates + 4 * 128 * 32, kDumpC = kDumpH + 128 * 32,
+              kDumpStep = kDumpC + 128 * 32;
+__device__ __forceinline__ void dump16(const TileArgs& a, long s, int region, int row, int half, const float (&v)[16], float inv_scale) {
+#if defined(SVAD_H16_DEBUG)
+    if (a.dbg && blockIdx.x == 0 && s < 2) {
+        float* d = reinterpret_cast<float*>(a.dbg) + s * kDumpStep + region + row * 32 + 16 * half;
+#pragma unroll
+        for (int i = 0; i < 16; i++) d[i] = v[i] * inv_scale;
+    }
+#endif
+}
+
+// barrier indices
+enum : int { kXpFull = 0, kStftAcc, kMagFull, kE0Acc, kE0Full, kFDone, kE1Ready, kE2Acc, kE2Full, kE3Acc, kE3Full, kLAcc,
+             kFFull0, kFEmpty0 = kFFull0 + kH16StagesF, kBFull0 = kFEmpty0 + kH16StagesF, kBEmpty0 = kBFull0 + kH16StagesB,
+             kNumBars = kBEmpty0 + kH16StagesB };
+
+// profiling stamps (debug buffer set): clock64 of CTA 0 at its middle step, [role 0..3 = EF, MF, EB, MB][16], after the dumps
+#define SVAD_H16_STAMP(role, k) do { if (c.stamps && s == c.stamp_step) c.stamps[(role) * 16 + (k)] = clock64(); } while (0)
+
+struct Ctx {
+    long long* stamps;   // null unless this thread records (one thread per role of CTA 0)
+    long stamp_step;
+    unsigned char* sm;
+    uint32_t sm32;       // shared-space address of sm
+    uint32_t bars;       // shared-space address of the barrier array
+    uint32_t tmem;
+    __device__ __forceinline__ uint32_t bar(int i) const { return bars + 8u * (uint32_t)i; }
+    __device__ __forceinline__ float* consts() const { return reinterpret_cast<float*>(sm + H16Map::C); }
+};
+
+// ================================================================ weight streams (one thread each)
+__device__ __forceinline__ void run_stream(const Ctx& c, const unsigned char* tape, long nsteps, int nslab, int slab_bytes, int nstages, int ring_off, int full0, int empty0) {
+    const long total = nsteps * nslab;
+    int idx = 0, stage = 0;
+    uint32_t round = 0;   // how often the ring has wrapped
+#pragma unroll 1
+    for (long i = 0; i < total; i++) {
+        if (round > 0) mbar_wait(c.bar(empty0 + stage), (round - 1) & 1u);
+        const uint32_t bar = c.bar(full0 + stage), dst = c.sm32 + (uint32_t)(ring_off + stage * slab_bytes);
+        mbar_expect_tx(bar, (uint32_t)slab_bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(tape + (size_t)idx * slab_bytes), "r"(slab_bytes), "r"(bar)
+                     : "memory");
+        if (++idx == nslab) idx = 0;
+        if (++stage == nstages) { stage = 0; round++; }
+    }
+}
+
+// ================================================================ MF: front MMA issue (one thread)
+template <bool SR16>
+__device__ __forceinline__ void run_mf(const Ctx& c, long nsteps) {
+    using G = H16Geo<SR16>;
+    using M = H16Map;
+    int stage = 0;        // front ring position and wrap parity
+    uint32_t round = 0;
+    auto slab = [&]() -> uint32_t {
+        mbar_wait(c.bar(kFFull0 + stage), round & 1u);
+        return c.sm32 + (uint32_t)(M::FR + stage * kH16SlabF);
+    };
+    auto slab_done = [&]() {
+        tc_commit(c.bar(kFEmpty0 + stage));
+        if (++stage == kH16StagesF) { stage = 0; round++; }
+    };
+    constexpr uint32_t xp_hi = M::R, xp_lo = M::R + G::XR * 64;
+    constexpr uint32_t mag_hi = M::R, mag_lo = M::R + 4 * G::Kt * 64;
+    constexpr uint32_t e0_hi = M::R, e0_lo = M::R + 32768;
+    for (long s = 0; s < nsteps; s++) {
+        const uint32_t par = (uint32_t)(s & 1);
+        // ---- STFT: D[row][frame*32 + slot] = sum_m basis[row][m] * xp[hop*frame + m][slot]; the four frames are N atoms `hop` rows apart
+        SVAD_H16_STAMP(1, 0);
+        mbar_wait(c.bar(kXpFull), par);
+        SVAD_H16_STAMP(1, 1);
+        if (s > 0) mbar_wait(c.bar(kE1Ready), par ^ 1u);   // enc1's accumulator of the previous step (columns 192..255) has been drained
+        SVAD_H16_STAMP(1, 2);
+        tc_after();
+        if constexpr (SR16) {
+#pragma unroll 1
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll 1
+                for (int kc = 0; kc < 4; kc++) {
+                    const uint64_t bh = desc_b(c.sm32 + xp_hi + kc * 4096, G::hop * 64), bl = desc_b(c.sm32 + xp_lo + kc * 4096, G::hop * 64);
+                    uint64_t a = desc_a(slab());                                     // w_hi . (x_hi, x_lo)
+                    mma_chunk<2>(c.tmem + 128 * mt, a, bh, a, bl, a, bl, idesc(128, 128), idesc(128, 128), kc != 0);
+                    slab_done();
+                    a = desc_a(slab());                                              // w_lo . x_hi
+                    mma_chunk<1>(c.tmem + 128 * mt, a, bh, a, bh, a, bh, idesc(128, 128), idesc(128, 128), true);
+                    slab_done();
+                }
+        } else {
+#pragma unroll 1
+            for (int kc = 0; kc < 2; kc++) {
+                const uint64_t bh = desc_b(c.sm32 + xp_hi + kc * 4096, G::hop * 64), bl = desc_b(c.sm32 + xp_lo + kc * 4096, G::hop * 64);
+#pragma unroll 1
+                for (int mt = 0; mt < 2; mt++) {
+                    const uint32_t w = slab();
+                    const uint64_t ah = desc_a(w), al = desc_a(w + 8192);
+                    mma_chunk<3>(c.tmem + 128 * mt, ah, bh, ah, bl, al, bh, idesc(64, 128), idesc(64, 128), kc != 0);
+                    slab_done();
+                }
+            }
+        }
+        tc_commit(c.bar(kStftAcc));
+        SVAD_H16_STAMP(1, 3);
+        // ---- enc0: out frame t reads in frame t + j - 1; tap order 1, 0, 2; one instruction covers every frame a tap reaches
+        mbar_wait(c.bar(kMagFull), par);
+        SVAD_H16_STAMP(1, 4);
+        tc_after();
+#pragma unroll 1
+        for (int jo = 0; jo < 3; jo++)
+            for (int ch = 0; ch < G::e0_chunks; ch++) {
+                const int j = jo == 0 ? 1 : (jo == 1 ? 0 : 2);
+                const int f0 = (j == 2) ? 1 : 0, nf = (j == 1) ? 4 : 3, t0 = f0 + 1 - j;
+                const uint32_t boff = (uint32_t)((f0 * G::Kt + 64 * ch) * 64);
+                const uint64_t bh = desc_b(c.sm32 + mag_hi + boff, G::Kt * 64), bl = desc_b(c.sm32 + mag_lo + boff, G::Kt * 64);
+                const uint32_t id = idesc(128, 32 * nf);
+                uint64_t a = desc_a(slab());
+                mma_chunk<2>(c.tmem + 32 * t0, a, bh, a, bl, a, bl, id, id, !(jo == 0 && ch == 0));
+                slab_done();
+                a = desc_a(slab());
+                mma_chunk<1>(c.tmem + 32 * t0, a, bh, a, bh, a, bh, id, id, true);
+                slab_done();
+            }
+        tc_commit(c.bar(kE0Acc));
+        SVAD_H16_STAMP(1, 5);
+        // ---- enc1 (M = 64, stride 2): out frame tt reads in frames 2 tt - 1 + j; taps 1 and 2 reach both output frames (N = 64, the
+        // two input frames are N atoms two frames apart), tap 0 only tt = 1 (frame -1 is the zero padding)
+        mbar_wait(c.bar(kE0Full), par);
+        SVAD_H16_STAMP(1, 6);
+        tc_after();
+#pragma unroll 1
+        for (int jo = 0; jo < 3; jo++) {
+            const int f0 = (jo == 0) ? 0 : 1, ncols = (jo == 2) ? 32 : 64, col = 192 + ((jo == 2) ? 32 : 0);
+            const uint32_t id = idesc(64, ncols);
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {
+                const uint32_t w = slab();
+                const uint64_t ah = desc_a(w), al = desc_a(w + 8192);
+                const uint32_t boff = (uint32_t)((f0 * 128 + 64 * ch) * 64);
+                const uint64_t bh = desc_b(c.sm32 + e0_hi + boff, 2 * 128 * 64), bl = desc_b(c.sm32 + e0_lo + boff, 2 * 128 * 64);
+                mma_chunk<3>(c.tmem + col, ah, bh, ah, bl, al, bh, id, id, !(jo == 0 && ch == 0));
+                slab_done();
+            }
+        }
+        tc_commit(c.bar(kFDone));   // enc1's accumulators are complete AND the front region is free for the next window
+        SVAD_H16_STAMP(1, 7);
+    }
+}
+
+// ================================================================ MB: back MMA issue (one thread)
+__device__ __forceinline__ void run_mb(const Ctx& c, long nsteps) {
+    using M = H16Map;
+    int stage = 0;
+    uint32_t round = 0;
+    auto slab = [&]() -> uint32_t {
+        mbar_wait(c.bar(kBFull0 + stage), round & 1u);
+        return c.sm32 + (uint32_t)(M::BR + stage * kH16SlabB);
+    };
+    auto slab_done = [&]() {
+        tc_commit(c.bar(kBEmpty0 + stage));
+        if (++stage == kH16StagesB) { stage = 0; round++; }
+    };
+    constexpr uint32_t e1_hi = M::P, e1_lo = M::P + 8192, e2_hi = M::P, e2_lo = M::P + 4096, e3_hi = M::P, h_hi = M::H;
+    for (long s = 0; s < nsteps; s++) {
+        const uint32_t par = (uint32_t)(s & 1);
+        // ---- enc2 (M = 64, N = 32): taps 1, 2 read e1 frames 0, 1
+        SVAD_H16_STAMP(3, 0);
+        mbar_wait(c.bar(kE1Ready), par);
+        SVAD_H16_STAMP(3, 1);
+        tc_after();
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            const uint32_t w = slab();
+            tc_after();
+            const uint64_t ah = desc_a(w), al = desc_a(w + 8192);
+            const uint64_t bh = desc_b(c.sm32 + e1_hi + q * 4096, 4096), bl = desc_b(c.sm32 + e1_lo + q * 4096, 4096);
+            mma_chunk<3>(c.tmem + 256, ah, bh, ah, bl, al, bh, idesc(64, 32), idesc(64, 32), q != 0);
+            slab_done();
+        }
+        tc_commit(c.bar(kE2Acc));
+        SVAD_H16_STAMP(3, 2);
+        // ---- enc3 (M = 128, N = 32, K = 64): slab 0 = w_hi (x_hi, x_lo), slab 1 = w_lo (x_hi)
+        mbar_wait(c.bar(kE2Full), par);
+        SVAD_H16_STAMP(3, 3);
+        tc_after();
+        {
+            uint32_t w = slab();
+            tc_after();
+            const uint64_t bh = desc_b(c.sm32 + e2_hi, 4096), bl = desc_b(c.sm32 + e2_lo, 4096);
+            uint64_t a = desc_a(w);
+            mma_chunk<2>(c.tmem + 288, a, bh, a, bl, a, bl, idesc(128, 32), idesc(128, 32), false);
+            slab_done();
+            w = slab();
+            tc_after();
+            a = desc_a(w);
+            mma_chunk<1>(c.tmem + 288, a, bh, a, bh, a, bh, idesc(128, 32), idesc(128, 32), true);
+            slab_done();
+        }
+        tc_commit(c.bar(kE3Acc));
+        SVAD_H16_STAMP(3, 4);
+        // ---- LSTM: gates[m*128 + j][slot] = sum_k W[.][k] * [e3 ; h][k][slot]; w_hi . [x_hi | x_lo] is one N = 64 instruction (the lo rows
+        // sit one N atom = 8 KB above the hi rows and land in the block's second 32 columns), w_lo . x_hi (N = 32) adds into the first 32
+        mbar_wait(c.bar(kE3Full), par);
+        SVAD_H16_STAMP(3, 5);
+        tc_after();
+#pragma unroll 1
+        for (int kc = 0; kc < 4; kc++) {
+            const uint32_t xrows = (kc < 2 ? e3_hi : h_hi) + (uint32_t)((kc & 1) * 4096);
+            const uint64_t bhl = desc_b(c.sm32 + xrows, 8192);
+#pragma unroll 1
+            for (int m = 0; m < 4; m++) {
+                uint32_t w = slab();
+                tc_after();
+                uint64_t a = desc_a(w);
+                mma_chunk<1>(c.tmem + 256 + 64 * m, a, bhl, a, bhl, a, bhl, idesc(128, 64), idesc(128, 64), kc != 0);
+                slab_done();
+                w = slab();
+                tc_after();
+                a = desc_a(w);
+                mma_chunk<1>(c.tmem + 256 + 64 * m, a, bhl, a, bhl, a, bhl, idesc(128, 32), idesc(128, 32), true);
+                slab_done();
+            }
+        }
+        tc_commit(c.bar(kLAcc));
+        SVAD_H16_STAMP(3, 6);
+    }
+}
+
+// ================================================================ EF: front epilogue group (warps 0-3)
+// Staging of the padded window [context | chunk | reflect pad] of chunk t into xp: a warp takes 32-row blocks, lane = row; 32
+// coalesced loads (one per slot) put row (m0 + lane) of all 32 slots into registers -- exactly one activation row -- which is
+// split and stored.  The loads of the warp's next block are issued before the current block is converted.
+template <bool SR16, typename S>
+__device__ __forceinline__ void stage_load(const S* p0, long ld, int nvalid, int blk, int lane, float (&v)[32]) {
+    using G = H16Geo<SR16>;
+    const int m = 32 * blk + lane;
+    const int src = (m >= G::L1) ? 2 * G::L1 - 2 - m : m;            // xp[L1 + j] = x1[L1 - 2 - j]
+    const S* p = p0 + src;
+#pragma unroll
+    for (int s = 0; s < 32; s++) v[s] = (s < nvalid) ? ld_sample(p + (long)s * ld) : 0.0f;
+}
+template <bool SR16>
+__device__ __forceinline__ void stage_store(const Ctx& c, int blk, int lane, const float (&v)[32]) {
+    using G = H16Geo<SR16>;
+    unsigned char* hi = c.sm + H16Map::R;
+    unsigned char* lo = c.sm + H16Map::R + G::XR * 64;
+#pragma unroll
+    for (int hf = 0; hf < 2; hf++) {
+        float w[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = v[16 * hf + i] * kSx;
+        store_row16(hi, lo, 32 * blk + lane, hf, w);
+    }
+}
+// first / last chunk of a row, or decimated input: context, zero tail and sample stride resolved per sample (cold path)
+template <bool SR16, typename S>
+__device__ __noinline__ void stage_generic(const Ctx& c, const TileArgs& a, const S* audio, int g0, int bt, long t, int warp, int lane) {
+    using G = H16Geo<SR16>;
+    unsigned char* hi = c.sm + H16Map::R;
+    unsigned char* lo = c.sm + H16Map::R + G::XR * 64;
+#pragma unroll 1
+    for (int blk = warp; blk < G::XR / 32; blk += 4) {
+        const int m = 32 * blk + lane;
+#pragma unroll 1
+        for (int hf = 0; hf < 2; hf++) {
+            float w[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int sl = 16 * hf + i, g = g0 + sl;
+                w[i] = (sl < bt && g < a.B) ? kSx * window_sample<SR16, S>(audio + (long)g * a.ld, a.L, a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr, t, m, a.dec) : 0.0f;
+            }
+            store_row16(hi, lo, m, hf, w);
+        }
+    }
+}
+
+template <bool SR16, typename S>
+__device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int first_tile, int tile_stride, int ntiles, int bt) {
+    using G = H16Geo<SR16>;
+    using M = H16Map;
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);   // warp 0..3 = TMEM lane quarter
+    const S* audio = static_cast<const S*>(a.audio);
+    const float* cs = c.consts();
+    float* nyq = c.consts() + M::c_nyq;
+    const float d_stft = cs[M::c_scale + 0], d_e0 = cs[M::c_scale + 1];
+    const uint32_t tq = c.tmem + ((uint32_t)(warp * 32) << 16);
+    // channel / bin owned by this thread
+    const int row = SR16 ? 32 * warp + lane : 16 * warp + (lane & 15);   // STFT bin (8 kHz: M = 64 accumulators keep row r in lane 32 (r / 16) + r % 16)
+    const bool stft_active = SR16 || lane < 16;
+    const int o = 32 * warp + lane;                                      // enc0 output channel
+    const float b0 = cs[M::c_b0 + o], wn0 = cs[M::c_wnyq + o], wn1 = cs[M::c_wnyq + 128 + o], wn2 = cs[M::c_wnyq + 256 + o];
+    long s = 0;
+    for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
+        const int g0 = tile * bt;
+        for (long t = 0; t < a.T; t++, s++) {
+            const uint32_t par = (uint32_t)(s & 1);
+            // ---- stage the window of chunk t (the front region is free once enc1 of the previous step has completed)
+            SVAD_H16_STAMP(0, 0);
+            if (s > 0) mbar_wait(c.bar(kFDone), par ^ 1u);
+            SVAD_H16_STAMP(0, 1);
+            {
+                const bool fast = (t > 0) && ((t + 1) * G::n <= a.L) && a.dec == 1;
+                if (t + 1 < a.T && a.dec == 1) {   // pull the next chunk of every stream of the tile into L2
+                    constexpr int kPerLine = 128 / (int)sizeof(S), kLines = G::n / kPerLine;
+#pragma unroll 1
+                    for (int i = (int)threadIdx.x; i < bt * kLines; i += 128) {
+                        const int loc = i / kLines, line = i % kLines, g = g0 + loc;
+                        const long off = (t + 1) * G::n + line * kPerLine;
+                        if (g < a.B && off < a.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(audio + (long)g * a.ld + off));
+                    }
+                }
+                if (fast) {
+                    constexpr int NB = G::XR / 32;   // 20 / 10 blocks, warp w takes w, w + 4, ...
+                    const S* p0 = audio + (long)g0 * a.ld + (t * G::n - G::ctx);
+                    const int nvalid = (a.B - g0 < bt) ? a.B - g0 : bt;
+                    float va[32], vb[32];
+                    stage_load<SR16, S>(p0, a.ld, nvalid, warp, lane, va);
+#pragma unroll 1
+                    for (int blk = warp; blk < NB; blk += 8) {
+                        if (blk + 4 < NB) stage_load<SR16, S>(p0, a.ld, nvalid, blk + 4, lane, vb);
+                        stage_store<SR16>(c, blk, lane, va);
+                        if (blk + 4 < NB) {
+                            if (blk + 8 < NB) stage_load<SR16, S>(p0, a.ld, nvalid, blk + 8, lane, va);
+                            stage_store<SR16>(c, blk + 4, lane, vb);
+                        }
+                    }
+                } else {
+                    stage_generic<SR16, S>(c, a, audio, g0, bt, t, warp, lane);
+                }
+            }
+            fence_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c.bar(kXpFull));
+            SVAD_H16_STAMP(0, 2);
+            // ---- STFT epilogue: |re + i im| -> mag rows (hi | lo); bin 0 and the Nyquist bin are real
+            mbar_wait(c.bar(kStftAcc), par);
+            SVAD_H16_STAMP(0, 3);
+            tc_after();
+            {
+                unsigned char* hi = c.sm + M::R;
+                unsigned char* lo = c.sm + M::R + 4 * G::Kt * 64;
+#pragma unroll 1
+                for (int f = 0; f < 4; f++) {
+                    float re[2][16], im[2][16];
+                    tmem_ld16(tq + (uint32_t)(f * 32), re[0]);
+                    tmem_ld16(tq + (uint32_t)(f * 32 + 16), re[1]);
+                    tmem_ld16(tq + (uint32_t)(128 + f * 32), im[0]);
+                    tmem_ld16(tq + (uint32_t)(128 + f * 32 + 16), im[1]);
+                    tmem_wait();
+                    if (stft_active) {
+#pragma unroll
+                        for (int hf = 0; hf < 2; hf++) {
+                            float mg[16];
+                            if (row == 0) {
+#pragma unroll
+                                for (int i = 0; i < 16; i++) { nyq[f * 32 + 16 * hf + i] = fabsf(im[hf][i]) * d_stft; mg[i] = fabsf(re[hf][i]) * (d_stft * kSmag); }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; i++) mg[i] = sqrt_fast(re[hf][i] * re[hf][i] + im[hf][i] * im[hf][i]) * (d_stft * kSmag);
+                            }
+                            store_row16(hi, lo, f * G::Kt + row, hf, mg);
+                            dump16(a, s, kDumpMag, f * G::Kt + row, hf, mg, 1.0f / kSmag);
+                        }
+                    }
+                }
+            }
+            tc_before();
+            fence_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c.bar(kMagFull));
+            SVAD_H16_STAMP(0, 4);
+            // ---- enc0 epilogue: + bias + Nyquist-bin rank-1 term (fp32), ReLU -> e0 rows (hi | lo)
+            mbar_wait(c.bar(kE0Acc), par);
+            SVAD_H16_STAMP(0, 5);
+            tc_after();
+            {
+                unsigned char* hi = c.sm + M::R;
+                unsigned char* lo = c.sm + M::R + 32768;
+#pragma unroll 1
+                for (int tt = 0; tt < 4; tt++) {
+                    float vv[2][16];
+                    tmem_ld16(tq + (uint32_t)(tt * 32), vv[0]);
+                    tmem_ld16(tq + (uint32_t)(tt * 32 + 16), vv[1]);
+                    tmem_wait();
+#pragma unroll
+                    for (int hf = 0; hf < 2; hf++) {
+                        float (&v)[16] = vv[hf];
+                        const float* ny = nyq + tt * 32 + 16 * hf;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            float acc = fmaf(v[i], d_e0, b0);
+                            if (tt > 0) acc = fmaf(wn0, ny[i - 32], acc);
+                            acc = fmaf(wn1, ny[i], acc);
+                            if (tt < 3) acc = fmaf(wn2, ny[i + 32], acc);
+                            v[i] = relu_f(acc) * kSe0;
+                        }
+                        store_row16(hi, lo, tt * 128 + o, hf, v);
+                        dump16(a, s, kDumpE0, tt * 128 + o, hf, v, 1.0f / kSe0);
+                    }
+                }
+            }
+            tc_before();
+            fence_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c.bar(kE0Full));
+            SVAD_H16_STAMP(0, 6);
+        }
+    }
+}
+
+// ================================================================ EB: back epilogue group (warps 4-7)
+template <bool SR16, typename S>
+__device__ __forceinline__ void run_eb(const Ctx& c, const TileArgs& a, int first_tile, int tile_stride, int ntiles, int bt) {
+    using G = H16Geo<SR16>;
+    using M = H16Map;
+    const int warp = (int)(threadIdx.x >> 5) - 4, lane = (int)(threadIdx.x & 31);   // warp 0..3 = TMEM lane quarter
+    const int tid = warp * 32 + lane;
+    const float* cs = c.consts();
+    const float d_e1 = cs[M::c_scale + 2], d_e2 = cs[M::c_scale + 3], d_e3 = cs[M::c_scale + 4], d_l = cs[M::c_scale + 5];
+    const uint32_t tq = c.tmem + ((uint32_t)(warp * 32) << 16);
+    const int o64 = 16 * warp + (lane & 15);   // channel of the M = 64 layers (lanes 0-15 of each quarter)
+    const bool act64 = lane < 16;
+    const int j = 32 * warp + lane;            // enc3 channel / LSTM hidden unit
+    const float b1 = cs[M::c_b1 + o64], b2 = cs[M::c_b2 + o64], b3 = cs[M::c_b3 + j];
+    const float bi = cs[M::c_bl + j], bf = cs[M::c_bl + 128 + j], bg = cs[M::c_bl + 256 + j], bo = cs[M::c_bl + 384 + j];
+    unsigned char* p_hi = c.sm + M::P;
+    unsigned char* h_hi = c.sm + M::H;
+    float creg[32], hreg[32];   // cell and hidden state of unit j for the 32 slots (fp32, never leave the registers between steps)
+    const S* audio = static_cast<const S*>(a.audio);
+    long s = 0;
+    for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
+        const int g0 = tile * bt;
+        // ---- tile start: carried-in state.  The previous tile's last LSTM MMAs have completed (this thread waited for them).
+#pragma unroll
+        for (int sl = 0; sl < 32; sl++) {
+            const int g = g0 + sl;
+            const bool v = a.state_in && sl < bt && g < a.B;
+            hreg[sl] = v ? a.state_in[(long)g * kHid + j] : 0.0f;
+            creg[sl] = v ? a.state_in[((long)a.B + g) * kHid + j] : 0.0f;
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = hreg[16 * hf + i] * kSh;
+            store_row16(h_hi, h_hi + 8192, j, hf, v);
+        }
+        for (long t = 0; t < a.T; t++, s++) {
+            const uint32_t par = (uint32_t)(s & 1);
+            // ---- enc1 epilogue: accumulator columns 192..255 (out frame tt at 32 tt) -> e1 [tt][64][32]
+            SVAD_H16_STAMP(2, 0);
+            mbar_wait(c.bar(kFDone), par);
+            SVAD_H16_STAMP(2, 1);
+            tc_after();
+#pragma unroll 1
+            for (int tt = 0; tt < 2; tt++) {
+                float vv[2][16];
+                tmem_ld16(tq + (uint32_t)(192 + tt * 32), vv[0]);
+                tmem_ld16(tq + (uint32_t)(192 + tt * 32 + 16), vv[1]);
+                tmem_wait();
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    float (&v)[16] = vv[hf];
+                    if (act64) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = relu_f(fmaf(v[i], d_e1, b1)) * kSe1;
+                        store_row16(p_hi, p_hi + 8192, tt * 64 + o64, hf, v);
+                        dump16(a, s, kDumpE1, tt * 64 + o64, hf, v, 1.0f / kSe1);
+                    }
+                }
+            }
+            tc_before();
+            fence_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c.bar(kE1Ready));
+            SVAD_H16_STAMP(2, 2);
+            // ---- enc2 epilogue: columns 256..287 -> e2 [64][32]
+            mbar_wait(c.bar(kE2Acc), par);
+            SVAD_H16_STAMP(2, 3);
+            tc_after();
+            {
+                float vv[2][16];
+                tmem_ld16(tq + 256u, vv[0]);
+                tmem_ld16(tq + 272u, vv[1]);
+                tmem_wait();
+#pragma unroll
+              for (int hf = 0; hf < 2; hf++) {
+                float (&v)[16] = vv[hf];
+                if (act64) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = relu_f(fmaf(v[i], d_e2, b2)) * kSe2;
+                    store_row16(p_hi, p_hi + 4096, o64, hf, v);
+                    dump16(a, s, kDumpE2, o64, hf, v, 1.0f / kSe2);
+                }
+              }
+            }
+            tc_before();
+            fence_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c.bar(kE2Full));
+            SVAD_H16_STAMP(2, 4);
+            // ---- enc3 epilogue: columns 288..319 -> e3 [128][32], the first half of the LSTM's K
+            mbar_wait(c.bar(kE3Acc), par);
+            SVAD_H16_STAMP(2, 5);
+            tc_after();
+            {
+                float vv[2][16];
+                tmem_ld16(tq + 288u, vv[0]);
+                tmem_ld16(tq + 304u, vv[1]);
+                tmem_wait();
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    float (&v)[16] = vv[hf];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = relu_f(fmaf(v[i], d_e3, b3)) * kSe3;
+                    store_row16(p_hi, p_hi + 8192, j, hf, v);
+                    dump16(a, s, kDumpE3, j, hf, v, 1.0f / kSe3);
+                }
+            }
+            tc_before();
+            fence_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c.bar(kE3Full));
+            SVAD_H16_STAMP(2, 6);
+            // ---- LSTM epilogue: gate math for hidden unit j, all 32 slots; c and h' stay in registers, h' also goes to the B rows
+            mbar_wait(c.bar(kLAcc), par);
+            SVAD_H16_STAMP(2, 7);
+            tc_after();
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {   // unrolled: creg / hreg are indexed statically and stay in registers
+                float gi[16], gf[16], gg[16], go[16], q[16];
+                {
+                    float q0[16];
+                    tmem_ld16(tq + (uint32_t)(256 + 0 * 64 + 16 * hf), gi); tmem_ld16(tq + (uint32_t)(256 + 0 * 64 + 32 + 16 * hf), q0);
+                    tmem_ld16(tq + (uint32_t)(256 + 1 * 64 + 16 * hf), gf); tmem_ld16(tq + (uint32_t)(256 + 1 * 64 + 32 + 16 * hf), q);
+                    tmem_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { gi[i] += q0[i]; gf[i] += q[i]; }
+                    tmem_ld16(tq + (uint32_t)(256 + 2 * 64 + 16 * hf), gg); tmem_ld16(tq + (uint32_t)(256 + 2 * 64 + 32 + 16 * hf), q0);
+                    tmem_ld16(tq + (uint32_t)(256 + 3 * 64 + 16 * hf), go); tmem_ld16(tq + (uint32_t)(256 + 3 * 64 + 32 + 16 * hf), q);
+                    tmem_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { gg[i] += q0[i]; go[i] += q[i]; }
+                }
+                dump16(a, s, kDumpGates + 0 * 4096, j, hf, gi, d_l); dump16(a, s, kDumpGates + 1 * 4096, j, hf, gf, d_l);
+                dump16(a, s, kDumpGates + 2 * 4096, j, hf, gg, d_l); dump16(a, s, kDumpGates + 3 * 4096, j, hf, go, d_l);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float ig = sigmoid_fast(fmaf(gi[i], d_l, bi)), fg = sigmoid_fast(fmaf(gf[i], d_l, bf));
+                    const float g2 = tanh_fast(fmaf(gg[i], d_l, bg)), og = sigmoid_fast(fmaf(go[i], d_l, bo));
+                    const float cn = fmaf(fg, creg[16 * hf + i], ig * g2);
+                    creg[16 * hf + i] = cn;
+                    const float hn = og * tanh_fast(cn);
+                    hreg[16 * hf + i] = hn;
+                    q[i] = hn * kSh;
+                }
+                store_row16(h_hi, h_hi + 8192, j, hf, q);
+                dump16(a, s, kDumpH, j, hf, q, 1.0f / kSh);
+            }
+            tc_before();
+            fence_async();
+            group_sync(1);   // every unit's h' row is in shared memory
+            SVAD_H16_STAMP(2, 8);
+            // ---- head: p = sigmoid(sum_j wout[j] relu(h'[j]) + bout); warp w takes slots 8w..8w+7, lane = (slot, quarter of the units)
+            {
+                const int sl = 8 * warp + (lane & 7), part = lane >> 3;
+                const __half* hh = reinterpret_cast<const __half*>(h_hi);
+                const __half* hl = reinterpret_cast<const __half*>(h_hi + 8192);
+                float acc = 0.0f;
+#pragma unroll 8
+                for (int u = 0; u < 32; u++) {
+                    const int r = 32 * part + u;
+                    const int pos = r * 32 + ((((sl >> 3) ^ ((r >> 1) & 3)) << 3) | (sl & 7));
+                    const float hv = (__half2float(hh[pos]) + __half2float(hl[pos])) * (1.0f / kSh);
+                    acc = fmaf(cs[M::c_wout + r], relu_f(hv), acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                const int g = g0 + sl;
+                if (part == 0 && sl < bt && g < a.B) a.probs[(long)g * a.ldp + t] = sigmoid_acc(acc + cs[M::c_bout]);
+            }
+            SVAD_H16_STAMP(2, 9);
+        }
+        // ---- tile end: carry state / context out
+        group_sync(1);   // the head of the last step has read every h row before the next tile's state overwrites them
+        if (a.state_out) {
+#pragma unroll
+            for (int sl = 0; sl < 32; sl++) {
+                const int g = g0 + sl;
+                if (sl < bt && g < a.B) {
+                    a.state_out[(long)g * kHid + j] = hreg[sl];
+                    a.state_out[((long)a.B + g) * kHid + j] = creg[sl];
+                }
+            }
+        }
+        if (a.ctx_out) {
+            for (int i = tid; i < bt * G::ctx; i += 128) {
+                const int loc = i / G::ctx, k = i % G::ctx, g = g0 + loc;
+                if (g < a.B) {
+                    const float* cx = a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr;
+                    a.ctx_out[(long)g * G::ctx + k] = (a.T > 0) ? window_sample<SR16, S>(audio + (long)g * a.ld, a.L, cx, a.T - 1, G::n + k, a.dec)
+                                                                : (cx ? cx[k] : 0.0f);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace h16
+
+// ================================================================ kernel
+template <bool SR16, typename S>
+__global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, const unsigned char* tapeF, const unsigned char* tapeB, int ntiles, int bt) {
+    using namespace h16;
+    using G = H16Geo<SR16>;
+    using M = H16Map;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    Ctx c;
+    c.stamps = nullptr;
+    c.stamp_step = -1;
+    c.sm = smem;
+    c.sm32 = s32(smem);
+    c.bars = c.sm32 + (uint32_t)M::BAR;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + M::BAR + 8 * kNumBars);
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    for (int i = (int)threadIdx.x; i < M::c_floats; i += kH16Threads) c.consts()[i] = a.consts[i];
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < kNumBars; b++) {
+            // group barriers: one arrival per warp of the 4-warp epilogue group; commit / TMA barriers: one arrival
+            const bool grp = (b == kXpFull || b == kMagFull || b == kE0Full || b == kE1Ready || b == kE2Full || b == kE3Full);
+            mbar_init(c.bar(b), grp ? 4u : 1u);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_before();
+    __syncthreads();
+    tc_after();
+    c.tmem = *tmem_slot;
+    int my_tiles = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
+    const long nsteps = (long)my_tiles * a.T;
+    if (a.dbg && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128 || (warp >= 8 && lane == 0))) {
+        c.stamps = a.dbg + (2 * h16::kDumpStep * 4 + 7) / 8;   // after the two activation dumps (floats), 8-byte aligned
+        c.stamp_step = nsteps / 2;
+    }
+    if (warp < 4) run_ef<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
+    else if (warp < 8) run_eb<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
+    else if (lane == 0) {
+        if (warp == 8) run_mf<SR16>(c, nsteps);
+        else if (warp == 9) run_mb(c, nsteps);
+        else if (warp == 10) run_stream(c, tapeF, nsteps, G::nslabF, kH16SlabF, kH16StagesF, M::FR, kFFull0, kFEmpty0);
+        else run_stream(c, tapeB, nsteps, G::nslabB, kH16SlabB, kH16StagesB, M::BR, kBFull0, kBEmpty0);
+    }
+    tc_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(512u) : "memory");
+}
+
+}  // namespace svad

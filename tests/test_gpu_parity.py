@@ -22,7 +22,7 @@ def torch_cuda():
     return torch
 
 
-@pytest.fixture(scope="module", params=["auto", "tc", "fp32"])
+@pytest.fixture(scope="module", params=["auto", "h16", "tc", "fp32"])
 def model(torch_cuda, request):
     """All kernels behind the same surface.  auto = the engine's defaults (small batches on the cluster kernel, large
     ones on the tensor-core tile kernel); tc / fp32 force the respective tile kernel for every batch size."""
