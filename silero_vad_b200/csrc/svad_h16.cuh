@@ -51,7 +51,7 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
 #pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); spin++) {
-        __nanosleep(32);
+        __nanosleep(64);
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
     }
@@ -62,11 +62,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (!done) mbar_wait_slow(bar, parity);
 }
+// The four single-thread roles (MMA issue, weight streams) poll without sleeping: their waits sit on the round trip of the weight
+// rings (slab landed -> MMAs issued -> committed -> next copy issued), where a 64 ns nap per hand-over is a tenth of the trip.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 28); spin++) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// The MMA-issue and weight-stream roles run as WHOLE, converged warps whose 32 lanes compute identical values; the one
+// instruction that must be issued once (tcgen05.mma / commit / the bulk copy) is predicated on elect.sync.  Run by a single lane of a
+// diverged warp instead, the descriptors live in per-thread registers and every tcgen05.mma is wrapped in a lane-broadcast loop
+// (ELECT / R2UR.BROADCAST / BRA.U.ANY): ~50 cycles of issue per instruction, as long as the instruction takes to execute.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    __syncwarp();
 }
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // one epilogue group
 
@@ -85,25 +106,25 @@ __device__ __forceinline__ constexpr uint32_t idesc(int M, int N) { return (1u <
 // C++ costs ~300 cycles each (tools/umma_f16_unit.cu), far above the 41-65 cycles the tensor pipe needs.
 // Pair 0 uses instruction descriptor i0, pairs 1 and 2 use i12 (the LSTM's w_lo . x_hi has another N).
 #define SVAD_H16_STEP(N) "add.s64 a0, %1, " #N "*2; add.s64 b0, %2, " #N "*64; add.s64 a1, %3, " #N "*2; add.s64 b1, %4, " #N "*64; add.s64 a2, %5, " #N "*2; add.s64 b2, %6, " #N "*64;\n"
-#define SVAD_H16_M0(P) "tcgen05.mma.cta_group::1.kind::f16 [%0], a0, b0, %7, " P ";\n"
-#define SVAD_H16_M1 "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %9, t;\n"
-#define SVAD_H16_M2 "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %9, t;\n"
+#define SVAD_H16_M0(P) "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a0, b0, %7, " P ";\n"
+#define SVAD_H16_M1 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %9, t;\n"
+#define SVAD_H16_M2 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %9, t;\n"
 template <int NP>
 __device__ __forceinline__ void mma_chunk(uint32_t d, uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1, uint64_t a2, uint64_t b2, uint32_t i0, uint32_t i12,
                                           bool acc_first) {
     const uint32_t accf = acc_first ? 1u : 0u;
     if constexpr (NP == 3) {
-        asm volatile("{\n.reg .pred p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
+        asm volatile("{\n.reg .pred q, p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
                      SVAD_H16_STEP(0) SVAD_H16_M0("p") SVAD_H16_M1 SVAD_H16_M2 SVAD_H16_STEP(1) SVAD_H16_M0("t") SVAD_H16_M1 SVAD_H16_M2
                      SVAD_H16_STEP(2) SVAD_H16_M0("t") SVAD_H16_M1 SVAD_H16_M2 SVAD_H16_STEP(3) SVAD_H16_M0("t") SVAD_H16_M1 SVAD_H16_M2 "}\n"
                      ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(i0), "r"(accf), "r"(i12) : "memory");
     } else if constexpr (NP == 2) {
-        asm volatile("{\n.reg .pred p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
+        asm volatile("{\n.reg .pred q, p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
                      SVAD_H16_STEP(0) SVAD_H16_M0("p") SVAD_H16_M1 SVAD_H16_STEP(1) SVAD_H16_M0("t") SVAD_H16_M1
                      SVAD_H16_STEP(2) SVAD_H16_M0("t") SVAD_H16_M1 SVAD_H16_STEP(3) SVAD_H16_M0("t") SVAD_H16_M1 "}\n"
                      ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(i0), "r"(accf), "r"(i12) : "memory");
     } else {
-        asm volatile("{\n.reg .pred p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
+        asm volatile("{\n.reg .pred q, p, t;\n.reg .b64 a0, b0, a1, b1, a2, b2;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %8, 0;\nsetp.eq.u32 t, %8, %8;\n"
                      SVAD_H16_STEP(0) SVAD_H16_M0("p") SVAD_H16_STEP(1) SVAD_H16_M0("t") SVAD_H16_STEP(2) SVAD_H16_M0("t") SVAD_H16_STEP(3) SVAD_H16_M0("t") "}\n"
                      ::"r"(d), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "r"(i0), "r"(accf), "r"(i12) : "memory");
     }
@@ -179,7 +200,7 @@ struct Ctx {
     uint32_t bars;       // shared-space address of the barrier array
     uint32_t tmem;
     __device__ __forceinline__ uint32_t bar(int i) const { return bars + 8u * (uint32_t)i; }
-    __device__ __forceinline__ float* consts() const { return reinterpret_cast<float*>(sm + H16Map::C); }
+    __device__ __forceinline__ float* scratch() const { return reinterpret_cast<float*>(sm + H16Map::C); }
 };
 
 // ================================================================ weight streams (one thread each)
@@ -189,12 +210,15 @@ __device__ __forceinline__ void run_stream(const Ctx& c, const unsigned char* ta
     uint32_t round = 0;   // how often the ring has wrapped
 #pragma unroll 1
     for (long i = 0; i < total; i++) {
-        if (round > 0) mbar_wait(c.bar(empty0 + stage), (round - 1) & 1u);
+        if (round > 0) mbar_wait_spin(c.bar(empty0 + stage), (round - 1) & 1u);
         const uint32_t bar = c.bar(full0 + stage), dst = c.sm32 + (uint32_t)(ring_off + stage * slab_bytes);
-        mbar_expect_tx(bar, (uint32_t)slab_bytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                     "l"(tape + (size_t)idx * slab_bytes), "r"(slab_bytes), "r"(bar)
-                     : "memory");
+        if (elect_one()) {
+            mbar_expect_tx(bar, (uint32_t)slab_bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(tape + (size_t)idx * slab_bytes), "r"(slab_bytes), "r"(bar)
+                         : "memory");
+        }
+        __syncwarp();
         if (++idx == nslab) idx = 0;
         if (++stage == nstages) { stage = 0; round++; }
     }
@@ -208,7 +232,7 @@ __device__ __forceinline__ void run_mf(const Ctx& c, long nsteps) {
     int stage = 0;        // front ring position and wrap parity
     uint32_t round = 0;
     auto slab = [&]() -> uint32_t {
-        mbar_wait(c.bar(kFFull0 + stage), round & 1u);
+        mbar_wait_spin(c.bar(kFFull0 + stage), round & 1u);
         return c.sm32 + (uint32_t)(M::FR + stage * kH16SlabF);
     };
     auto slab_done = [&]() {
@@ -306,7 +330,7 @@ __device__ __forceinline__ void run_mb(const Ctx& c, long nsteps) {
     int stage = 0;
     uint32_t round = 0;
     auto slab = [&]() -> uint32_t {
-        mbar_wait(c.bar(kBFull0 + stage), round & 1u);
+        mbar_wait_spin(c.bar(kBFull0 + stage), round & 1u);
         return c.sm32 + (uint32_t)(M::BR + stage * kH16SlabB);
     };
     auto slab_done = [&]() {
@@ -316,37 +340,32 @@ __device__ __forceinline__ void run_mb(const Ctx& c, long nsteps) {
     constexpr uint32_t e1_hi = M::P, e1_lo = M::P + 8192, e2_hi = M::P, e2_lo = M::P + 4096, e3_hi = M::P, h_hi = M::H;
     for (long s = 0; s < nsteps; s++) {
         const uint32_t par = (uint32_t)(s & 1);
-        // ---- enc2 (M = 64, N = 32): taps 1, 2 read e1 frames 0, 1
+        // ---- enc2 (M = 64, N = 32): taps 1, 2 read e1 frames 0, 1; one slab = both taps {hi | lo}
         SVAD_H16_STAMP(3, 0);
         mbar_wait(c.bar(kE1Ready), par);
         SVAD_H16_STAMP(3, 1);
         tc_after();
-#pragma unroll 1
-        for (int q = 0; q < 2; q++) {
+        {
             const uint32_t w = slab();
-            tc_after();
-            const uint64_t ah = desc_a(w), al = desc_a(w + 8192);
-            const uint64_t bh = desc_b(c.sm32 + e1_hi + q * 4096, 4096), bl = desc_b(c.sm32 + e1_lo + q * 4096, 4096);
-            mma_chunk<3>(c.tmem + 256, ah, bh, ah, bl, al, bh, idesc(64, 32), idesc(64, 32), q != 0);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint64_t ah = desc_a(w + q * 16384), al = desc_a(w + q * 16384 + 8192);
+                const uint64_t bh = desc_b(c.sm32 + e1_hi + q * 4096, 4096), bl = desc_b(c.sm32 + e1_lo + q * 4096, 4096);
+                mma_chunk<3>(c.tmem + 256, ah, bh, ah, bl, al, bh, idesc(64, 32), idesc(64, 32), q != 0);
+            }
             slab_done();
         }
         tc_commit(c.bar(kE2Acc));
         SVAD_H16_STAMP(3, 2);
-        // ---- enc3 (M = 128, N = 32, K = 64): slab 0 = w_hi (x_hi, x_lo), slab 1 = w_lo (x_hi)
+        // ---- enc3 (M = 128, N = 32, K = 64): one slab {w_hi | w_lo}
         mbar_wait(c.bar(kE2Full), par);
         SVAD_H16_STAMP(3, 3);
         tc_after();
         {
-            uint32_t w = slab();
-            tc_after();
+            const uint32_t w = slab();
             const uint64_t bh = desc_b(c.sm32 + e2_hi, 4096), bl = desc_b(c.sm32 + e2_lo, 4096);
-            uint64_t a = desc_a(w);
-            mma_chunk<2>(c.tmem + 288, a, bh, a, bl, a, bl, idesc(128, 32), idesc(128, 32), false);
-            slab_done();
-            w = slab();
-            tc_after();
-            a = desc_a(w);
-            mma_chunk<1>(c.tmem + 288, a, bh, a, bh, a, bh, idesc(128, 32), idesc(128, 32), true);
+            const uint64_t ah = desc_a(w), al = desc_a(w + 16384);
+            mma_chunk<3>(c.tmem + 288, ah, bh, ah, bl, al, bh, idesc(128, 32), idesc(128, 32), false);
             slab_done();
         }
         tc_commit(c.bar(kE3Acc));
@@ -362,15 +381,9 @@ __device__ __forceinline__ void run_mb(const Ctx& c, long nsteps) {
             const uint64_t bhl = desc_b(c.sm32 + xrows, 8192);
 #pragma unroll 1
             for (int m = 0; m < 4; m++) {
-                uint32_t w = slab();
-                tc_after();
-                uint64_t a = desc_a(w);
-                mma_chunk<1>(c.tmem + 256 + 64 * m, a, bhl, a, bhl, a, bhl, idesc(128, 64), idesc(128, 64), kc != 0);
-                slab_done();
-                w = slab();
-                tc_after();
-                a = desc_a(w);
-                mma_chunk<1>(c.tmem + 256 + 64 * m, a, bhl, a, bhl, a, bhl, idesc(128, 32), idesc(128, 32), true);
+                const uint32_t w = slab();
+                const uint64_t ah = desc_a(w), al = desc_a(w + 16384);
+                mma_chunk<2>(c.tmem + 256 + 64 * m, ah, bhl, al, bhl, al, bhl, idesc(128, 64), idesc(128, 32), kc != 0);
                 slab_done();
             }
         }
@@ -405,6 +418,66 @@ __device__ __forceinline__ void stage_store(const Ctx& c, int blk, int lane, con
         store_row16(hi, lo, 32 * blk + lane, hf, w);
     }
 }
+// Vector variant (rows 16-byte aligned: ld % 4 == 0): a warp block is still 32 rows x 32 slots, but lane (rg = lane & 7, cg = lane >> 3)
+// loads 4 consecutive samples (rows 4 rg .. 4 rg + 3) of the 8 slots 8 cg .. 8 cg + 7 with eight 16-byte loads -- a 4 x 8 patch whose
+// rows are whole 16-byte chunks of activation rows.  A quarter of the load instructions of the scalar variant, which was
+// instruction-bound (address arithmetic), not latency-bound.  The four row stores are issued in an order that depends on the
+// parity of rg so that one store instruction covers both halves of the 128-byte bank lines (4 wavefronts instead of 8).
+__device__ __forceinline__ void ld4(const float* p, float (&x)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+__device__ __forceinline__ void ld4(const int16_t* p, float (&x)[4]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    x[0] = (float)(int16_t)(v.x & 0xffffu) * (1.0f / 32768.0f); x[1] = (float)(int16_t)(v.x >> 16) * (1.0f / 32768.0f);
+    x[2] = (float)(int16_t)(v.y & 0xffffu) * (1.0f / 32768.0f); x[3] = (float)(int16_t)(v.y >> 16) * (1.0f / 32768.0f);
+}
+template <typename S>
+__device__ __forceinline__ void stagev_load(const S* p0, long ld, int nvalid, int blk, int lane, float (&v)[8][4]) {
+    const int rg = lane & 7, cg = lane >> 3;
+    const S* p = p0 + 32 * blk + 4 * rg + (long)(8 * cg) * ld;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (8 * cg + j < nvalid) ld4(p, v[j]);
+        else { v[j][0] = 0.0f; v[j][1] = 0.0f; v[j][2] = 0.0f; v[j][3] = 0.0f; }
+        p += ld;
+    }
+}
+template <bool SR16>
+__device__ __forceinline__ void stagev_store(const Ctx& c, int blk, int lane, const float (&v)[8][4]) {
+    using G = H16Geo<SR16>;
+    const int rg = lane & 7, cg = lane >> 3;
+    unsigned char* hi = c.sm + H16Map::R;
+    const bool odd = rg & 1;
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {   // row pairs (0, 1), (2, 3): odd row groups store the pair in swapped order
+        uint32_t h[2][4], l[2][4];
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int w = 0; w < 4; w++) split2(v[2 * w][2 * pr + k] * kSx, v[2 * w + 1][2 * pr + k] * kSx, h[k][w], l[k][w]);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int row = 32 * blk + 4 * rg + 2 * pr + (i ^ (int)odd);
+            const int off = row * 64 + ((cg ^ ((row >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(hi + off) = odd ? make_uint4(h[i ^ 1][0], h[i ^ 1][1], h[i ^ 1][2], h[i ^ 1][3]) : make_uint4(h[i][0], h[i][1], h[i][2], h[i][3]);
+            *reinterpret_cast<uint4*>(hi + G::XR * 64 + off) = odd ? make_uint4(l[i ^ 1][0], l[i ^ 1][1], l[i ^ 1][2], l[i ^ 1][3]) : make_uint4(l[i][0], l[i][1], l[i][2], l[i][3]);
+        }
+    }
+}
+// reflect pad rows xp[L1 + i] = xp[L1 - 2 - i], i < N / 4, copied inside shared memory (hi and lo images, re-swizzled per row)
+template <bool SR16>
+__device__ __forceinline__ void stage_reflect(const Ctx& c, int tid) {
+    using G = H16Geo<SR16>;
+#pragma unroll 1
+    for (int idx = tid; idx < (G::N / 4) * 8; idx += 128) {
+        const int arr = idx & 1, ch = (idx >> 1) & 3, i = idx >> 3;
+        const int src = G::L1 - 2 - i, dst = G::L1 + i;
+        unsigned char* base = c.sm + H16Map::R + arr * (G::XR * 64);
+        *reinterpret_cast<uint4*>(base + dst * 64 + ((ch ^ ((dst >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(base + src * 64 + ((ch ^ ((src >> 1) & 3)) << 4));
+    }
+}
+
 // first / last chunk of a row, or decimated input: context, zero tail and sample stride resolved per sample (cold path)
 template <bool SR16, typename S>
 __device__ __noinline__ void stage_generic(const Ctx& c, const TileArgs& a, const S* audio, int g0, int bt, long t, int warp, int lane) {
@@ -433,8 +506,8 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
     using M = H16Map;
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);   // warp 0..3 = TMEM lane quarter
     const S* audio = static_cast<const S*>(a.audio);
-    const float* cs = c.consts();
-    float* nyq = c.consts() + M::c_nyq;
+    const float* cs = a.consts;   // global; everything needed is read into registers here
+    float* nyq = c.scratch() + M::s_nyq;
     const float d_stft = cs[M::c_scale + 0], d_e0 = cs[M::c_scale + 1];
     const uint32_t tq = c.tmem + ((uint32_t)(warp * 32) << 16);
     // channel / bin owned by this thread
@@ -442,6 +515,7 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
     const bool stft_active = SR16 || lane < 16;
     const int o = 32 * warp + lane;                                      // enc0 output channel
     const float b0 = cs[M::c_b0 + o], wn0 = cs[M::c_wnyq + o], wn1 = cs[M::c_wnyq + 128 + o], wn2 = cs[M::c_wnyq + 256 + o];
+    const bool vec_ok = (a.ld % 4 == 0) && (reinterpret_cast<uintptr_t>(audio) % (4 * sizeof(S)) == 0);   // rows start on 4-sample boundaries
     long s = 0;
     for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
         const int g0 = tile * bt;
@@ -462,7 +536,24 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
                         if (g < a.B && off < a.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(audio + (long)g * a.ld + off));
                     }
                 }
-                if (fast) {
+                if (fast && vec_ok) {
+                    constexpr int NB = G::L1 / 32;   // 18 / 9 blocks of [context | chunk]; the reflect rows are copied afterwards
+                    const S* p0 = audio + (long)g0 * a.ld + (t * G::n - G::ctx);
+                    const int nvalid = (a.B - g0 < bt) ? a.B - g0 : bt;
+                    float va[8][4], vb[8][4];
+                    stagev_load<S>(p0, a.ld, nvalid, warp, lane, va);
+#pragma unroll 1
+                    for (int blk = warp; blk < NB; blk += 8) {
+                        if (blk + 4 < NB) stagev_load<S>(p0, a.ld, nvalid, blk + 4, lane, vb);
+                        stagev_store<SR16>(c, blk, lane, va);
+                        if (blk + 4 < NB) {
+                            if (blk + 8 < NB) stagev_load<S>(p0, a.ld, nvalid, blk + 8, lane, va);
+                            stagev_store<SR16>(c, blk + 4, lane, vb);
+                        }
+                    }
+                    group_sync(2);
+                    stage_reflect<SR16>(c, (int)threadIdx.x);
+                } else if (fast) {
                     constexpr int NB = G::XR / 32;   // 20 / 10 blocks, warp w takes w, w + 4, ...
                     const S* p0 = audio + (long)g0 * a.ld + (t * G::n - G::ctx);
                     const int nvalid = (a.B - g0 < bt) ? a.B - g0 : bt;
@@ -568,7 +659,9 @@ __device__ __forceinline__ void run_eb(const Ctx& c, const TileArgs& a, int firs
     using M = H16Map;
     const int warp = (int)(threadIdx.x >> 5) - 4, lane = (int)(threadIdx.x & 31);   // warp 0..3 = TMEM lane quarter
     const int tid = warp * 32 + lane;
-    const float* cs = c.consts();
+    const float* cs = a.consts;
+    const float* wout = c.scratch() + M::s_wout;
+    const float bout = cs[M::c_bout];
     const float d_e1 = cs[M::c_scale + 2], d_e2 = cs[M::c_scale + 3], d_e3 = cs[M::c_scale + 4], d_l = cs[M::c_scale + 5];
     const uint32_t tq = c.tmem + ((uint32_t)(warp * 32) << 16);
     const int o64 = 16 * warp + (lane & 15);   // channel of the M = 64 layers (lanes 0-15 of each quarter)
@@ -725,12 +818,12 @@ __device__ __forceinline__ void run_eb(const Ctx& c, const TileArgs& a, int firs
                     const int r = 32 * part + u;
                     const int pos = r * 32 + ((((sl >> 3) ^ ((r >> 1) & 3)) << 3) | (sl & 7));
                     const float hv = (__half2float(hh[pos]) + __half2float(hl[pos])) * (1.0f / kSh);
-                    acc = fmaf(cs[M::c_wout + r], relu_f(hv), acc);
+                    acc = fmaf(wout[r], relu_f(hv), acc);
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 8);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 16);
                 const int g = g0 + sl;
-                if (part == 0 && sl < bt && g < a.B) a.probs[(long)g * a.ldp + t] = sigmoid_acc(acc + cs[M::c_bout]);
+                if (part == 0 && sl < bt && g < a.B) a.probs[(long)g * a.ldp + t] = sigmoid_acc(acc + bout);
             }
             SVAD_H16_STAMP(2, 9);
         }
@@ -775,8 +868,8 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
     c.sm32 = s32(smem);
     c.bars = c.sm32 + (uint32_t)M::BAR;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + M::BAR + 8 * kNumBars);
-    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
-    for (int i = (int)threadIdx.x; i < M::c_floats; i += kH16Threads) c.consts()[i] = a.consts[i];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = (int)(threadIdx.x & 31);   // warp-uniform by construction
+    if (threadIdx.x < 128) c.scratch()[M::s_wout + threadIdx.x] = a.consts[M::c_wout + threadIdx.x];
     if (threadIdx.x == 0) {
         for (int b = 0; b < kNumBars; b++) {
             // group barriers: one arrival per warp of the 4-warp epilogue group; commit / TMA barriers: one arrival
@@ -797,18 +890,16 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
     const long nsteps = (long)my_tiles * a.T;
-    if (a.dbg && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128 || (warp >= 8 && lane == 0))) {
+    if (a.dbg && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128 || (warp >= 8 && warp < 10 && lane == 0))) {
         c.stamps = a.dbg + (2 * h16::kDumpStep * 4 + 7) / 8;   // after the two activation dumps (floats), 8-byte aligned
         c.stamp_step = nsteps / 2;
     }
     if (warp < 4) run_ef<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
     else if (warp < 8) run_eb<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
-    else if (lane == 0) {
-        if (warp == 8) run_mf<SR16>(c, nsteps);
-        else if (warp == 9) run_mb(c, nsteps);
-        else if (warp == 10) run_stream(c, tapeF, nsteps, G::nslabF, kH16SlabF, kH16StagesF, M::FR, kFFull0, kFEmpty0);
-        else run_stream(c, tapeB, nsteps, G::nslabB, kH16SlabB, kH16StagesB, M::BR, kBFull0, kBEmpty0);
-    }
+    else if (warp == 8) run_mf<SR16>(c, nsteps);
+    else if (warp == 9) run_mb(c, nsteps);
+    else if (warp == 10) run_stream(c, tapeF, nsteps, G::nslabF, kH16SlabF, kH16StagesF, M::FR, kFFull0, kFEmpty0);
+    else run_stream(c, tapeB, nsteps, G::nslabB, kH16SlabB, kH16StagesB, M::BR, kBFull0, kBEmpty0);
     tc_before();
     __syncthreads();
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(512u) : "memory");

@@ -46,10 +46,12 @@ struct H16Geo {
     static constexpr int nslab_e0 = 3 * e0_chunks * 2;   // (tap, chunk) x {hi, lo}
     static constexpr int nslab_e1 = 6;               // (tap, chunk): {hi | lo} of a [64 x 64] tile
     static constexpr int nslabF = nslab_stft + nslab_e0 + nslab_e1;   // 34 / 16 slabs per chunk step
-    static constexpr int nslabB = 2 + 2 + 32;                         // enc2 (2), enc3 (hi, lo), LSTM (16 x {hi, lo}): 16 KB each
+    static constexpr int nslabB = 1 + 1 + 16;                         // enc2 (both taps), enc3 {hi | lo}, LSTM 16 x {hi | lo}: 32 KB each
 };
-constexpr int kH16SlabF = 16384, kH16SlabB = 16384;
-constexpr int kH16StagesF = 3, kH16StagesB = 3;
+// One thread issues a bulk copy about every 310 cycles whatever its size (tools/ubench_feed.cu: 16 KB copies 52 B/clk/SM, 32 KB copies
+// 78-96 B/clk/SM, ceiling ~105-110): the back tape, dominated by the LSTM's 512 KB per step, moves in 32 KB slabs.
+constexpr int kH16SlabF = 16384, kH16SlabB = 32768;
+constexpr int kH16StagesF = 3, kH16StagesB = 2;
 constexpr int kH16Threads = 384;   // warps 0-3 front epilogue, 4-7 back epilogue, 8 / 9 MMA issue (front / back), 10 / 11 weight streams
 
 // activation scales (exact powers of two).  |x| <= 1 for normalised audio; mag <= 181 |x|; e0..e3 were observed <= 72 on speech
@@ -67,11 +69,13 @@ struct H16Map {
     static constexpr int H_bytes = 16384;
     static constexpr int FR = H + H_bytes;            // front weight ring
     static constexpr int BR = FR + kH16StagesF * kH16SlabF;
-    static constexpr int C = BR + kH16StagesB * kH16SlabB;   // constants (floats)
-    static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_wnyq = 1024, c_nyq = 1408,
+    static constexpr int C = BR + kH16StagesB * kH16SlabB;   // shared-memory scratch (floats): |X| of the Nyquist bin [4 frames][32], head weights
+    static constexpr int s_nyq = 0, s_wout = 128, s_floats = 256;
+    // constants block in GLOBAL memory (biases and scales are read once per thread into registers)
+    static constexpr int c_b0 = 0, c_b1 = 128, c_b2 = 192, c_b3 = 256, c_bl = 384, c_wout = 896, c_wnyq = 1024,
                          c_bout = 1536, c_scale = 1540;      // c_scale: d_stft, d_e0, d_e1, d_e2, d_e3, d_lstm
     static constexpr int c_floats = 1552;
-    static constexpr int BAR = C + c_floats * 4;      // mbarriers + TMEM slot
+    static constexpr int BAR = C + s_floats * 4;      // mbarriers + TMEM slot
     static constexpr int total = BAR + 512;
 };
 static_assert(H16Map::FR % 1024 == 0 && H16Map::BR % 1024 == 0 && H16Map::P % 1024 == 0 && H16Map::H % 1024 == 0, "tile alignment");
@@ -179,15 +183,15 @@ inline bool pack_branch_h16(const TensorMap& tm, PackedH16& out, std::string& er
     }
     // ---- back tape: enc2 (taps 1, 2: tap 0 only ever multiplies zero padding), enc3 (tap 1), LSTM
     for (int q = 0; q < 2; q++) {
-        unsigned char* s = tb + (size_t)q * kH16SlabB;
+        unsigned char* s = tb + (size_t)q * 16384;   // slab 0: tap 1 {hi | lo}, tap 2 {hi | lo}
         h16_pack_tile(64, [&](int o, int k) { return (double)w2[((size_t)o * 64 + k) * 3 + q + 1]; }, S2, s, s + 8192);
     }
-    h16_pack_tile(128, [&](int o, int k) { return (double)w3[((size_t)o * 64 + k) * 3 + 1]; }, S3, tb + 2 * kH16SlabB, tb + 3 * kH16SlabB);
+    h16_pack_tile(128, [&](int o, int k) { return (double)w3[((size_t)o * 64 + k) * 3 + 1]; }, S3, tb + kH16SlabB, tb + kH16SlabB + 16384);
     for (int kc = 0; kc < 4; kc++)
         for (int m = 0; m < 4; m++) {
-            unsigned char* s = tb + (size_t)(4 + (kc * 4 + m) * 2) * kH16SlabB;
+            unsigned char* s = tb + (size_t)(2 + kc * 4 + m) * kH16SlabB;
             const float* src = kc < 2 ? wih : whh;
-            h16_pack_tile(128, [&](int j, int k) { return (double)src[(size_t)(m * 128 + j) * 128 + 64 * (kc & 1) + k]; }, Sl, s, s + kH16SlabB);
+            h16_pack_tile(128, [&](int j, int k) { return (double)src[(size_t)(m * 128 + j) * 128 + 64 * (kc & 1) + k]; }, Sl, s, s + 16384);
         }
     // ---- constants
     out.consts.assign(H16Map::c_floats, 0.0f);
