@@ -45,9 +45,13 @@ void svad_engine_destroy(svad_engine* e);
 
 /* Streams per CTA tile = 4*rows; rows in [4,8], 0 = choose per call (default). Testing / tuning knob. */
 int svad_engine_set_tile_rows(svad_engine* e, int rows);
-/* Kernel selection: 1 = tensor-core kernel (default: tcgen05, split-precision TF32 for the four encoder convolutions
- * and the LSTM cell; STFT, gate math and head fp32 on the CUDA cores), 0 = all-fp32 CUDA-core kernel.  Both meet the
- * parity bar; their probabilities differ by ~5e-6, the carried cell state by ~5e-6 relative. */
+/* Kernel selection for batches above the small-batch limit:
+ *   2 = svad_fused_h16 (default): every contraction, the STFT included (as the reference's dense DFT-basis product), on tcgen05 with
+ *       fp16 split-precision operands (x.w = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, fp32 accumulate in TMEM), two software-pipelined
+ *       loops per CTA;
+ *   1 = svad_fused_tc: encoder + LSTM on tcgen05 with tf32 split precision, STFT as an FFT on the CUDA cores;
+ *   0 = svad_fused_fp32: all-fp32 CUDA-core kernel.
+ * All meet the parity bar; their probabilities differ by ~5e-6. */
 int svad_engine_set_kernel(svad_engine* e, int kernel);
 /* Batches of up to `streams` streams run on the small-batch cluster kernel (8-CTA clusters with the network split
  * across their shared memories; the latency path).  Default 256 (measured crossover with the tile kernels); 0 disables it. */
@@ -98,6 +102,21 @@ int svad_forward_host_pcm16(svad_engine* e, int sr, int B, int64_t L, int64_t ld
                             const float* ctx_in, float* state_out, float* ctx_out, float* probs, int64_t ldp);
 int svad_step_host(svad_engine* e, int sr, int B, const float* input, const float* state_in, float* prob,
                    float* state_out);
+
+/* ---- persistent streaming session (low-latency path, BASELINE configs[1]) ------------------------------
+ * Replaces the reference's per-chunk streaming call, one model invocation + `.item()` per 32 ms chunk
+ * (src/silero_vad/utils_vad.py:507-549 VADIterator.__call__; examples/cpp/silero-vad-onnx.cpp:167-197 predict()): one cluster of
+ * 8 CTAs stays resident on the GPU with the whole network in its shared memory and (h, c) + audio context on chip, and is fed
+ * through a mailbox in mapped pinned host memory.  svad_stream_push costs one PCIe round trip plus the compute: no kernel launch,
+ * no cudaMemcpy, no stream synchronisation per chunk.  Up to 4 streams per session (they advance together, one chunk each per push).
+ * The session occupies 8 SMs until closed; the kernel ends by itself after ~30 s without a chunk (push then reports an error). */
+typedef struct svad_stream svad_stream;
+int svad_stream_open(svad_engine* e, int sr, int nstreams, svad_stream** out);
+/* chunk f32[nstreams][n] (host, n = 512 @16 kHz / 256 @8 kHz) -> prob f32[nstreams]; state and context carry over between pushes */
+int svad_stream_push(svad_stream* s, const float* chunk, float* prob);
+/* forget (h, c) and the context before the next chunk (model.reset_states(), utils_vad.py:51-55) */
+int svad_stream_reset(svad_stream* s);
+int svad_stream_close(svad_stream* s);
 
 /* ---- speech segments from probabilities (host; the automaton of get_speech_timestamps) -------------
  * Replaces: src/silero_vad/utils_vad.py:315-319,338-440 (one stream) and the native port

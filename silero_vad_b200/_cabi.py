@@ -13,7 +13,7 @@ _lib = None
 EXPORTS = ["svad_abi_version", "svad_last_error", "svad_engine_create", "svad_engine_destroy",
            "svad_engine_set_tile_rows", "svad_engine_set_kernel", "svad_engine_set_small_batch_max", "svad_engine_sm_count", "svad_engine_launch_count",
            "svad_forward_device", "svad_forward_device_pcm16", "svad_forward_device_ex", "svad_step_device", "svad_forward_host",
-           "svad_collect_chunks_device",
+           "svad_collect_chunks_device", "svad_stream_open", "svad_stream_push", "svad_stream_reset", "svad_stream_close",
            "svad_forward_host_pcm16", "svad_step_host",
            "svad_segment_params_default", "svad_speech_segments"]
 
@@ -55,6 +55,10 @@ def lib():
     L.svad_forward_device_pcm16.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]
     L.svad_forward_host_pcm16.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64]
     L.svad_forward_device_ex.argtypes = [vp, i32, i32, i64, i64, vp, i32, i32, vp, vp, vp, vp, vp, i64, vp]
+    L.svad_stream_open.argtypes = [vp, i32, i32, ctypes.POINTER(vp)]
+    L.svad_stream_push.argtypes = [vp, vp, vp]
+    L.svad_stream_reset.argtypes = [vp]
+    L.svad_stream_close.argtypes = [vp]
     L.svad_collect_chunks_device.argtypes = [vp, vp, i32, i64, i64, vp, vp, vp, i64, i32, vp, i64, vp, vp]
     L.svad_step_device.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.svad_forward_host.argtypes = [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, i64]
@@ -132,6 +136,26 @@ class Engine:
                                                seg_bounds.ctypes.data, len(seg_rows), 1 if drop else 0, out_ptr, out_cap,
                                                offs.ctypes.data, stream))
         return offs
+
+    # ---- persistent streaming session (svad_stream_*): chunk in, probability out, no launch per chunk
+    def stream_open(self, sr, nstreams=1):
+        h = ctypes.c_void_p()
+        check(lib().svad_stream_open(self._h, sr, nstreams, ctypes.byref(h)))
+        return h
+
+    def stream_push(self, h, chunk):
+        """chunk: C-contiguous float32 numpy [nstreams, n] (or [n]); returns float32 numpy [nstreams]."""
+        import numpy as np
+        chunk = np.ascontiguousarray(chunk, np.float32)
+        prob = np.zeros(max(1, chunk.shape[0] if chunk.ndim == 2 else 1), np.float32)
+        check(lib().svad_stream_push(h, chunk.ctypes.data, prob.ctypes.data))
+        return prob
+
+    def stream_reset(self, h):
+        check(lib().svad_stream_reset(h))
+
+    def stream_close(self, h):
+        check(lib().svad_stream_close(h))
 
     def forward_host_pcm16(self, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp):
         check(lib().svad_forward_host_pcm16(self._h, sr, B, L, ld, audio, state_in, ctx_in, state_out, ctx_out, probs, ldp))

@@ -13,6 +13,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+#include <chrono>
 #include <exception>
 #include <new>
 #include <string>
@@ -342,8 +344,20 @@ __global__ void __launch_bounds__(kThreads, 1) svad_fused_tc(TileArgs a, int nti
 // ------------------------------------------------------------------------------------------ small-batch cluster kernel
 namespace cg = cooperative_groups;
 
-template <bool SR16, typename S>
-__global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs a, const float* __restrict__ blobs) {
+// Mailbox of the persistent single-cluster variant (svad_stream_*): mapped pinned host memory.  The host writes chunk `q` into
+// in[q % kMailRing] and publishes seq_in = q + 1; every CTA of the cluster polls seq_in, builds the window from the mailbox and its
+// own copy of the carried context, and rank 0 answers with out[q % kMailRing] and seq_out = q + 1.  seq_in < 0 ends the kernel.
+constexpr int kMailRing = 4;
+struct SmallMail {
+    volatile long long* seq_in;    // host -> device
+    volatile long long* seq_out;   // device -> host
+    volatile int* flags;           // [kMailRing] bit 0: reset state and context before this chunk
+    const float* in;               // [kMailRing][kSmallNS][n]
+    volatile float* out;           // [kMailRing][kSmallNS]
+};
+
+template <bool SR16, typename S, bool MB = false>
+__global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs a, const float* __restrict__ blobs, SmallMail mb = SmallMail{}) {
     using G = Geo<SR16>;
     using M = SmallMap<SR16>;
     extern __shared__ __align__(16) float sm[];
@@ -391,15 +405,53 @@ __global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs 
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
 #define SM_STAMP(k) do { if (a.dbg && blockIdx.x == 0 && t == 2 && tid == 0) a.dbg[k] = clock64(); } while (0)
-    for (long t = 0; t < a.T; t++) {
+    float* ctxbuf = sm + M::total_floats;   // mailbox mode: carried context [ctx][4]
+    __shared__ int s_cmd;
+    if (MB) for (int i = tid; i < G::ctx * 4; i += kSmallThreads) ctxbuf[i] = 0.0f;
+    for (long t = 0; MB || t < a.T; t++) {
         const int cur = (int)(t & 1);
         SM_STAMP(0);
+        if constexpr (MB) {
+            // rank 0 waits for chunk t (a PCIe read per poll paces the loop; ~30 s without a chunk ends the kernel) and hands the
+            // command word to all 8 CTAs through distributed shared memory, so the cluster takes every decision together
+            if (r == 0 && tid == 0) {
+                int cmd = -1;
+                for (long spin = 0; spin < (1L << 24); spin++) {
+                    const long long v = *mb.seq_in;
+                    if (v < 0) break;
+                    if (v > t) { cmd = mb.flags[t % kMailRing]; break; }
+                }
+#pragma unroll
+                for (int q = 0; q < kSmallCtas; q++) *cluster.map_shared_rank(&s_cmd, q) = cmd;
+            }
+            cluster.sync();
+            const int cmd = s_cmd;
+            if (cmd < 0) break;
+            if (cmd & 1) {        // new call on this line: zero (h, c) and the context
+                for (int i = tid; i < G::ctx * 4; i += kSmallThreads) ctxbuf[i] = 0.0f;
+                for (int i = tid; i < 128 * 4; i += kSmallThreads) hbuf[cur][i] = 0.0f;
+                if (tid < 64) sm[M::a_c + tid] = 0.0f;
+            }
+            __syncthreads();
+            const float* chunk = mb.in + (size_t)(t % kMailRing) * kSmallNS * G::n;
+            for (int i = tid; i < (G::L1 + G::N / 4) * 4; i += kSmallThreads) {
+                int k = i >> 2;
+                const int st = i & 3;
+                if (k >= G::L1) k = 2 * G::L1 - 2 - k;
+                float v = 0.0f;
+                if (st < a.B) v = (k < G::ctx) ? ctxbuf[k * 4 + st] : __ldcv(chunk + st * G::n + (k - G::ctx));
+                sm[M::a_xp + i] = v;
+            }
+            __syncthreads();
+            for (int i = tid; i < G::ctx * 4; i += kSmallThreads) ctxbuf[i] = sm[M::a_xp + (G::L1 - G::ctx) * 4 + i];
+        } else {
         // 1. padded window [context | chunk | reflect] of the 4 streams
         for (int i = tid; i < (G::L1 + G::N / 4) * 4; i += kSmallThreads) {
             const int k = i >> 2, st = i & 3, g = g0 + st;
             float v = 0.0f;
             if (g < a.B) v = window_sample<SR16, S>(audio + (long)g * a.ld, a.L, a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr, t, k, a.dec);
             sm[M::a_xp + i] = v;
+        }
         }
         __syncthreads();
         SM_STAMP(1);
@@ -543,7 +595,13 @@ __global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs 
                 const float b = sm[M::w_out + 128];
                 if (tid < kSmallNS && g0 + tid < a.B) {
                     const float x = tid == 0 ? v.x : (tid == 1 ? v.y : (tid == 2 ? v.z : v.w));
-                    a.probs[(long)(g0 + tid) * a.ldp + t] = sigmoid_acc(x + b);
+                    if constexpr (MB) mb.out[(t % kMailRing) * kSmallNS + tid] = sigmoid_acc(x + b);
+                    else a.probs[(long)(g0 + tid) * a.ldp + t] = sigmoid_acc(x + b);
+                }
+                if constexpr (MB) {   // publish: probabilities first, then the sequence number the host spins on
+                    __threadfence_system();
+                    __syncwarp();
+                    if (tid == 0) *mb.seq_out = t + 1;
                 }
             }
         }
@@ -605,7 +663,7 @@ struct svad_engine {
     float* d_h16_c[2] = {nullptr, nullptr};
     float* d_small[2] = {nullptr, nullptr};    // small-batch cluster kernel: 8 per-CTA weight slices
     int small_max = 256;                       // streams up to which the cluster kernel is used (0 = never); crossover with the tile kernels measured at ~256
-    int kernel = 1;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32, 2 = tcgen05 split-fp16 two-loop kernel
+    int kernel = 2;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32, 2 = tcgen05 split-fp16 two-loop kernel (default)
     long long* dbg = nullptr;
     int64_t launches = 0;
     // staging for the host-buffer entry points
@@ -779,7 +837,7 @@ static int launch_small(svad_engine* e, const TileArgs& a, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = kSmallCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, (const float*)e->d_small[SR16 ? 0 : 1]));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, (const float*)e->d_small[SR16 ? 0 : 1], SmallMail{}));
     e->launches++;
     return SVAD_OK;
 }
@@ -1122,4 +1180,121 @@ extern "C" int svad_collect_chunks_device(svad_engine* e, const void* d_wav, int
     } catch (const std::bad_alloc&) {
         return fail(SVAD_ENOMEM, "out of memory");
     }
+}
+
+// ------------------------------------------------------------------------------------------ persistent streaming (BASELINE configs[1])
+// One cluster of 8 CTAs stays resident and serves up to 4 live streams chunk by chunk through a mailbox in mapped pinned memory:
+// no kernel launch, no cudaMemcpy and no stream synchronisation per 32 ms chunk -- the caller of the reference's streaming loop
+// (VADIterator.__call__, src/silero_vad/utils_vad.py:507-549: one model call + .item() per chunk) pays one PCIe round trip.
+struct svad_stream {
+    svad_engine* e = nullptr;
+    int sr = 0, ns = 0, n = 0;
+    cudaStream_t st = nullptr;
+    unsigned char* host = nullptr;
+    SmallMail dev{};
+    volatile long long* seq_in = nullptr;
+    volatile long long* seq_out = nullptr;
+    volatile int* flags = nullptr;
+    float* in = nullptr;
+    volatile float* out = nullptr;
+    long long seq = 0;
+    bool reset_next = true, dead = false;
+};
+
+template <bool SR16>
+static int launch_stream_kernel(svad_stream* s) {
+    auto kern = svad_small_cluster<SR16, float, true>;
+    const size_t smem = (size_t)SmallMap<SR16>::total_floats * 4 + (size_t)Geo<SR16>::ctx * 4 * 4;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TileArgs a{};
+    a.B = s->ns; a.dec = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kSmallCtas);
+    cfg.blockDim = dim3(kSmallThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kSmallCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, (const float*)s->e->d_small[SR16 ? 0 : 1], s->dev));
+    s->e->launches++;
+    return SVAD_OK;
+}
+
+extern "C" int svad_stream_close(svad_stream* s) {
+    if (!s) return SVAD_OK;
+    if (s->seq_in) {
+        std::atomic_thread_fence(std::memory_order_release);
+        *s->seq_in = -1;
+    }
+    if (s->st) { cudaStreamSynchronize(s->st); cudaStreamDestroy(s->st); }
+    if (s->host) cudaFreeHost(s->host);
+    delete s;
+    return SVAD_OK;
+}
+
+extern "C" int svad_stream_open(svad_engine* e, int sr, int nstreams, svad_stream** out) {
+    if (!e || !out) return fail(SVAD_EINVAL, "null argument");
+    *out = nullptr;
+    if (sr != 16000 && sr != 8000) return fail(SVAD_EINVAL, "Supported sampling rates: [8000, 16000] (got %d)", sr);
+    if (nstreams < 1 || nstreams > kSmallNS) return fail(SVAD_EINVAL, "a streaming session serves 1..%d streams", kSmallNS);
+    CUDA_TRY(cudaSetDevice(e->device));
+    svad_stream* s = new (std::nothrow) svad_stream();
+    if (!s) return fail(SVAD_ENOMEM, "out of memory");
+    s->e = e; s->sr = sr; s->ns = nstreams; s->n = sr == 16000 ? 512 : 256;
+    const size_t in_bytes = (size_t)kMailRing * kSmallNS * s->n * 4, bytes = 256 + in_bytes + (size_t)kMailRing * kSmallNS * 4;
+    int rc = SVAD_OK;
+    do {
+        if (cudaHostAlloc((void**)&s->host, bytes, cudaHostAllocMapped) != cudaSuccess) { rc = fail(SVAD_ENOMEM, "cudaHostAlloc(mapped) failed"); break; }
+        memset(s->host, 0, bytes);
+        unsigned char* d = nullptr;
+        if (cudaHostGetDevicePointer((void**)&d, s->host, 0) != cudaSuccess) { rc = fail(SVAD_ECUDA, "cudaHostGetDevicePointer failed"); break; }
+        s->seq_in = reinterpret_cast<volatile long long*>(s->host);
+        s->seq_out = reinterpret_cast<volatile long long*>(s->host + 64);
+        s->flags = reinterpret_cast<volatile int*>(s->host + 128);
+        s->in = reinterpret_cast<float*>(s->host + 256);
+        s->out = reinterpret_cast<volatile float*>(s->host + 256 + in_bytes);
+        s->dev.seq_in = reinterpret_cast<volatile long long*>(d);
+        s->dev.seq_out = reinterpret_cast<volatile long long*>(d + 64);
+        s->dev.flags = reinterpret_cast<volatile int*>(d + 128);
+        s->dev.in = reinterpret_cast<const float*>(d + 256);
+        s->dev.out = reinterpret_cast<volatile float*>(d + 256 + in_bytes);
+        if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SVAD_ECUDA, "cudaStreamCreate failed"); break; }
+        rc = sr == 16000 ? launch_stream_kernel<true>(s) : launch_stream_kernel<false>(s);
+    } while (0);
+    if (rc != SVAD_OK) { s->seq_in = nullptr; svad_stream_close(s); return rc; }
+    *out = s;
+    return SVAD_OK;
+}
+
+extern "C" int svad_stream_reset(svad_stream* s) {
+    if (!s) return fail(SVAD_EINVAL, "null stream");
+    s->reset_next = true;   // applied by the kernel before the next chunk
+    return SVAD_OK;
+}
+
+// chunk f32[nstreams][n] (host) -> prob f32[nstreams]; blocks until the persistent kernel has answered (one PCIe round trip + ~13 us of compute)
+extern "C" int svad_stream_push(svad_stream* s, const float* chunk, float* prob) {
+    if (!s || !chunk || !prob) return fail(SVAD_EINVAL, "null argument");
+    if (s->dead) return fail(SVAD_ECUDA, "streaming session has ended (timed out); open a new one");
+    const int slot = (int)(s->seq % kMailRing);
+    float* dst = s->in + (size_t)slot * kSmallNS * s->n;
+    memcpy(dst, chunk, (size_t)s->ns * s->n * 4);
+    s->flags[slot] = s->reset_next ? 1 : 0;
+    s->reset_next = false;
+    std::atomic_thread_fence(std::memory_order_release);
+    *s->seq_in = s->seq + 1;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 1;; spin++) {
+        if (*s->seq_out == s->seq + 1) break;
+        if ((spin & 0xFFFF) == 0) {
+            if (cudaStreamQuery(s->st) != cudaErrorNotReady) { s->dead = true; return fail(SVAD_ECUDA, "the persistent streaming kernel is not running any more"); }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) { s->dead = true; return fail(SVAD_ECUDA, "streaming kernel did not answer within 10 s"); }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int i = 0; i < s->ns; i++) prob[i] = s->out[slot * kSmallNS + i];
+    s->seq++;
+    return SVAD_OK;
 }

@@ -158,11 +158,60 @@ class SileroVADB200:
             context = context.detach().to(device=self.device, dtype=torch.float32, copy=True).contiguous()
         self._state, self._context, self._last_sr, self._last_batch_size = state, context, last_sr, last_bs
 
+    def stream(self, sr: int = 16000, nstreams: int = 1):
+        """A persistent low-latency session (svad_stream_*): a duck-typed model object for `VADIterator` and other chunk-by-chunk
+        callers whose `__call__` costs one PCIe round trip instead of a launch + two copies + a sync."""
+        return StreamSession(self, sr, nstreams)
+
     def eval(self):
         return self
 
     def to(self, *args, **kwargs):
         return self
+
+
+class StreamSession:
+    """model(chunk, sr) / reset_states() over a resident cluster kernel fed through mapped host memory.  Same protocol as the
+    reference model object for streaming callers (utils_vad.py:507-549): chunks of exactly n samples, float32, [n] or [nstreams, n];
+    returns a CPU tensor [nstreams, 1].  Close it (or use it as a context manager) to release its 8 SMs."""
+    sample_rates = [8000, 16000]
+
+    def __init__(self, model, sr, nstreams):
+        if sr not in self.sample_rates:
+            raise ValueError(f"Supported sampling rates: {self.sample_rates}")
+        self.engine, self.sr, self.nstreams = model.engine, sr, nstreams
+        self.n = 512 if sr == 16000 else 256
+        self._h = self.engine.stream_open(sr, nstreams)
+
+    def reset_states(self, batch_size=1):
+        self.engine.stream_reset(self._h)
+
+    def __call__(self, x, sr: int):
+        if sr != self.sr:
+            raise ValueError(f"this session runs at {self.sr} Hz")
+        x = torch.as_tensor(x, dtype=torch.float32)
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        if x.dim() != 2 or x.shape[0] != self.nstreams or x.shape[1] != self.n:
+            raise ValueError(f"Provided number of samples is {x.shape[-1]} (Supported values: 256 for 8000 sample rate, 512 for 16000)")
+        return torch.from_numpy(self.engine.stream_push(self._h, x.contiguous().numpy())).unsqueeze(1)
+
+    def close(self):
+        if self._h is not None:
+            self.engine.stream_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def load_silero_vad(onnx=False, opset_version=16, device=None):

@@ -172,8 +172,10 @@ def test_full_size_batch_property(torch_cuda, model, fixtures, request):
     p = p.view(512, 8, -1)
     assert bool((p == p[0:1]).all())
     single = torch.stack([model.audio_forward(a[i:i + 1], 16000)[0] for i in range(8)])
-    if request.node.callspec.params["model"] == "auto":   # B=1 runs on the cluster kernel, B=4096 on the tile kernel
-        assert float((p[0].cpu() - single).abs().max()) < TIGHT
+    if request.node.callspec.params["model"] == "auto":   # B=1 runs on the fp32 cluster kernel, B=4096 on the default tile kernel:
+        d = float((p[0].cpu() - single).abs().max())      # two implementations, each within TIGHT of the reference
+        print(f"tile kernel vs cluster kernel: {d:.3e}")
+        assert d < 2 * TIGHT
     else:
         assert bool((p[0].cpu() == single).all())
 

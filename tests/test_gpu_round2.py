@@ -282,3 +282,37 @@ def test_collect_and_drop_chunks(torch_cuda, model, fixtures, r2meta):
             parts.append(rows[b][: lens[b]][cur: d["start"]]); cur = d["end"]
         parts.append(rows[b][: lens[b]][cur:])
         assert torch.equal(got[b].cpu(), torch.cat(parts)), b
+
+
+@pytest.mark.parametrize("name", ["test16k", "aepyx8k"])
+def test_persistent_stream_session(torch_cuda, fixtures, meta, name):
+    """svad_stream_*: the resident cluster kernel fed through mapped host memory gives the reference's chunk-by-chunk probabilities,
+    drives VADIterator to the reference's events, resets, and serves several streams in one session."""
+    torch = torch_cuda
+    from silero_vad_b200 import VADIterator, load_silero_vad
+    fx = fixtures[name]
+    sr, n = fx["sr"], 512 if fx["sr"] == 16000 else 256
+    wav = torch.from_numpy(fx["audio"])
+    m = load_silero_vad(device=0)
+    T = 400
+    with m.stream(sr) as ses:
+        for rep in range(2):   # second pass after a reset gives the same values
+            p = np.asarray([float(ses(wav[t * n:(t + 1) * n], sr)) for t in range(T)], np.float32)
+            err = float(np.abs(p - fx["probs"][:T]).max())
+            print(f"stream session {name} pass {rep}: max|p - p_ref| = {err:.3e}")
+            assert err < TIGHT
+            ses.reset_states()
+        if name == "test16k":
+            it = VADIterator(ses)
+            ev = [e for e in (it(wav[i:i + 512]) for i in range(0, 512 * 600, 512)) if e]
+            want = meta["test16k"]["vad_iterator_events"]
+            assert ev == want[:len(ev)] and len(ev) > 6
+        with pytest.raises(ValueError):
+            ses(wav[:100], sr)
+    with m.stream(sr, nstreams=3) as ses:
+        offs = [0, 40000, 90000]
+        got = np.stack([ses(torch.stack([wav[o + t * n: o + (t + 1) * n] for o in offs]), sr).numpy()[:, 0] for t in range(60)], 1)
+        want = m.audio_forward(torch.stack([wav[o: o + 60 * n] for o in offs]), sr).numpy()
+        assert float(np.abs(got - want).max()) < TIGHT
+    # the engine still serves ordinary calls while / after sessions
+    assert float(np.abs(m.audio_forward(wav[None, : n * 50], sr).numpy()[0] - fx["probs"][:50]).max()) < TIGHT
