@@ -407,22 +407,49 @@ __global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs 
 #define SM_STAMP(k) do { if (a.dbg && blockIdx.x == 0 && t == 2 && tid == 0) a.dbg[k] = clock64(); } while (0)
     float* ctxbuf = sm + M::total_floats;   // mailbox mode: carried context [ctx][4]
     __shared__ int s_cmd;
-    if (MB) for (int i = tid; i < G::ctx * 4; i += kSmallThreads) ctxbuf[i] = 0.0f;
+    if (MB) {
+        for (int i = tid; i < G::ctx * 4; i += kSmallThreads) ctxbuf[i] = 0.0f;
+        for (int i = tid; i < (G::L1 + G::N / 4) * 4; i += kSmallThreads) sm[M::a_xp + i] = 0.0f;   // slots of absent streams stay zero
+        __syncthreads();
+        cluster.sync();
+    }
     for (long t = 0; MB || t < a.T; t++) {
         const int cur = (int)(t & 1);
         SM_STAMP(0);
         if constexpr (MB) {
-            // rank 0 waits for chunk t (a PCIe read per poll paces the loop; ~30 s without a chunk ends the kernel) and hands the
-            // command word to all 8 CTAs through distributed shared memory, so the cluster takes every decision together
-            if (r == 0 && tid == 0) {
-                int cmd = -1;
-                for (long spin = 0; spin < (1L << 24); spin++) {
-                    const long long v = *mb.seq_in;
-                    if (v < 0) break;
-                    if (v > t) { cmd = mb.flags[t % kMailRing]; break; }
+            // Rank 0 waits for chunk t -- ONE mailbox word carries the sequence number and the reset bit, a PCIe read per poll paces
+            // the loop, ~30 s without a chunk ends the kernel -- fetches the samples with coalesced 16-byte reads (a few dozen PCIe
+            // transactions instead of thousands of 4-byte ones) and writes them, with the command, into all 8 CTAs through
+            // distributed shared memory: the cluster takes every decision together.
+            if (r == 0) {
+                if (tid == 0) {
+                    int cmd = -1;
+                    for (long spin = 0; spin < (1L << 24); spin++) {
+                        const long long v = *mb.seq_in;
+                        if (v < 0) break;
+                        if ((v >> 1) > t) { cmd = (int)(v & 1); break; }
+                    }
+                    s_cmd = cmd;
                 }
+                __syncthreads();
+                const int cmd0 = s_cmd;
+                if (cmd0 >= 0) {
+                    const float4* chunk4 = reinterpret_cast<const float4*>(mb.in + (size_t)(t % kMailRing) * kSmallNS * G::n);
+                    for (int idx = tid; idx < a.B * (G::n / 4); idx += kSmallThreads) {
+                        const int st = idx / (G::n / 4), kk = (idx % (G::n / 4)) * 4;
+                        const float4 v = __ldcv(chunk4 + st * (G::n / 4) + kk / 4);
+                        const int off = M::a_xp + (G::ctx + kk) * 4 + st;
 #pragma unroll
-                for (int q = 0; q < kSmallCtas; q++) *cluster.map_shared_rank(&s_cmd, q) = cmd;
+                        for (int q = 0; q < kSmallCtas; q++) {
+                            float* d = peer[q] + off;
+                            d[0] = v.x; d[4] = v.y; d[8] = v.z; d[12] = v.w;
+                        }
+                    }
+                }
+                if (tid == 0) {
+#pragma unroll
+                    for (int q = 1; q < kSmallCtas; q++) *cluster.map_shared_rank(&s_cmd, q) = cmd0;
+                }
             }
             cluster.sync();
             const int cmd = s_cmd;
@@ -431,16 +458,13 @@ __global__ void __launch_bounds__(kSmallThreads, 1) svad_small_cluster(TileArgs 
                 for (int i = tid; i < G::ctx * 4; i += kSmallThreads) ctxbuf[i] = 0.0f;
                 for (int i = tid; i < 128 * 4; i += kSmallThreads) hbuf[cur][i] = 0.0f;
                 if (tid < 64) sm[M::a_c + tid] = 0.0f;
+                __syncthreads();
             }
-            __syncthreads();
-            const float* chunk = mb.in + (size_t)(t % kMailRing) * kSmallNS * G::n;
-            for (int i = tid; i < (G::L1 + G::N / 4) * 4; i += kSmallThreads) {
-                int k = i >> 2;
-                const int st = i & 3;
-                if (k >= G::L1) k = 2 * G::L1 - 2 - k;
-                float v = 0.0f;
-                if (st < a.B) v = (k < G::ctx) ? ctxbuf[k * 4 + st] : __ldcv(chunk + st * G::n + (k - G::ctx));
-                sm[M::a_xp + i] = v;
+            // context rows from the carried copy, reflect rows xp[L1 + j] = xp[L1 - 2 - j] from the chunk rows just delivered
+            for (int i = tid; i < G::ctx * 4; i += kSmallThreads) sm[M::a_xp + i] = ctxbuf[i];
+            for (int i = tid; i < (G::N / 4) * 4; i += kSmallThreads) {
+                const int j = i >> 2, st = i & 3;
+                sm[M::a_xp + (G::L1 + j) * 4 + st] = sm[M::a_xp + (G::L1 - 2 - j) * 4 + st];
             }
             __syncthreads();
             for (int i = tid; i < G::ctx * 4; i += kSmallThreads) ctxbuf[i] = sm[M::a_xp + (G::L1 - G::ctx) * 4 + i];
@@ -1281,10 +1305,10 @@ extern "C" int svad_stream_push(svad_stream* s, const float* chunk, float* prob)
     const int slot = (int)(s->seq % kMailRing);
     float* dst = s->in + (size_t)slot * kSmallNS * s->n;
     memcpy(dst, chunk, (size_t)s->ns * s->n * 4);
-    s->flags[slot] = s->reset_next ? 1 : 0;
+    const long long word = ((s->seq + 1) << 1) | (s->reset_next ? 1 : 0);   // sequence number and reset bit travel in ONE word
     s->reset_next = false;
     std::atomic_thread_fence(std::memory_order_release);
-    *s->seq_in = s->seq + 1;
+    *s->seq_in = word;
     const auto t0 = std::chrono::steady_clock::now();
     for (unsigned spin = 1;; spin++) {
         if (*s->seq_out == s->seq + 1) break;
