@@ -47,7 +47,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // Between polls the thread sleeps ~32 ns: twelve warps share four schedulers, and a waiter that polls flat out takes issue
 // slots (and the pipe SYNCS runs on) from the warps doing the epilogue math -- measured: 58 % of all executed instructions were
 // spin-loop instructions and every phase ran 3x slower than alone.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
 #pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); spin++) {
@@ -156,7 +156,12 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
     hi = h; lo = l;
 }
 // 16 consecutive slots [16*half, +16) of activation row `row` (already scaled) -> the row's hi and lo images (row pitch 64 B)
-__device__ __forceinline__ void store_row16(unsigned char* hi_base, unsigned char* lo_base, int row, int half, const float (&v)[16]) {
+#if defined(SVAD_H16_NOINLINE_STORE)   // measured: 1.86e8 -> 1.38e8 (the 16 values go through local memory)
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void store_row16(unsigned char* hi_base, unsigned char* lo_base, int row, int half, const float (&v)[16]) {
     uint32_t h[8], l[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
@@ -523,10 +528,18 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
             const uint32_t par = (uint32_t)(s & 1);
             // ---- stage the window of chunk t (the front region is free once enc1 of the previous step has completed)
             SVAD_H16_STAMP(0, 0);
+            const bool fast = (t > 0) && ((t + 1) * G::n <= a.L) && a.dec == 1;
+            float va[8][4], vb[8][4];
+            const S* p0 = audio + (long)g0 * a.ld + (t * G::n - G::ctx);
+            const int nvalid = (a.B - g0 < bt) ? a.B - g0 : bt;
+            // the first two blocks of this warp are loaded while enc1 of the previous step still owns the front region
+            if (fast && vec_ok) {
+                stagev_load<S>(p0, a.ld, nvalid, warp, lane, va);
+                stagev_load<S>(p0, a.ld, nvalid, warp + 4, lane, vb);
+            }
             if (s > 0) mbar_wait(c.bar(kFDone), par ^ 1u);
             SVAD_H16_STAMP(0, 1);
             {
-                const bool fast = (t > 0) && ((t + 1) * G::n <= a.L) && a.dec == 1;
                 if (t + 1 < a.T && a.dec == 1) {   // pull the next chunk of every stream of the tile into L2
                     constexpr int kPerLine = 128 / (int)sizeof(S), kLines = G::n / kPerLine;
 #pragma unroll 1
@@ -537,18 +550,14 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
                     }
                 }
                 if (fast && vec_ok) {
-                    constexpr int NB = G::L1 / 32;   // 18 / 9 blocks of [context | chunk]; the reflect rows are copied afterwards
-                    const S* p0 = audio + (long)g0 * a.ld + (t * G::n - G::ctx);
-                    const int nvalid = (a.B - g0 < bt) ? a.B - g0 : bt;
-                    float va[8][4], vb[8][4];
-                    stagev_load<S>(p0, a.ld, nvalid, warp, lane, va);
+                    constexpr int NB = G::L1 / 32;   // 18 / 9 blocks of [context | chunk] (every warp has >= 2); the reflect rows are copied afterwards
 #pragma unroll 1
                     for (int blk = warp; blk < NB; blk += 8) {
-                        if (blk + 4 < NB) stagev_load<S>(p0, a.ld, nvalid, blk + 4, lane, vb);
                         stagev_store<SR16>(c, blk, lane, va);
+                        if (blk + 8 < NB) stagev_load<S>(p0, a.ld, nvalid, blk + 8, lane, va);
                         if (blk + 4 < NB) {
-                            if (blk + 8 < NB) stagev_load<S>(p0, a.ld, nvalid, blk + 8, lane, va);
                             stagev_store<SR16>(c, blk + 4, lane, vb);
+                            if (blk + 12 < NB) stagev_load<S>(p0, a.ld, nvalid, blk + 12, lane, vb);
                         }
                     }
                     group_sync(2);
