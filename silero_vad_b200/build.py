@@ -13,7 +13,7 @@ LIB = PKG / "lib" / "libsilero_vad_b200.so"
 SOURCES = [PKG / "csrc" / "svad_api.cu", PKG / "csrc" / "svad_segments.cpp"]
 HEADERS = sorted((PKG / "csrc").glob("*.h")) + sorted((PKG / "csrc").glob("*.cuh")) + [PKG.parent / "include" / "silero_vad_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xptxas", "-v"] + os.environ.get("SVAD_EXTRA_NVCC", "").split()
 HASH = PKG / "lib" / "source_hash.txt"
 
 

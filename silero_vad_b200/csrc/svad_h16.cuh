@@ -70,6 +70,9 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; spin < (1u << 28); spin++) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
+#if defined(SVAD_H16_SPIN_NAP)
+        __nanosleep(SVAD_H16_SPIN_NAP);
+#endif
     }
     __trap();
 }
@@ -173,6 +176,12 @@ void store_row16(unsigned char* hi_base, unsigned char* lo_base, int row, int ha
     *reinterpret_cast<uint4*>(lo_base + row * 64 + c1) = make_uint4(l[4], l[5], l[6], l[7]);
 }
 __device__ __forceinline__ float relu_f(float v) { return v > 0.0f ? v : 0.0f; }
+// Gate activations from one MUFU.EX2 and one MUFU.RCP each (no Newton step: rcp.approx is good to 1 ulp, the results enter products
+// that are split to 22 bits anyway); exact saturation: 2^x = inf -> rcp = 0.
+__device__ __forceinline__ float rcp_approx(float y) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sigmoid_mufu(float v) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }
+__device__ __forceinline__ float tanh_mufu(float v) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * v)), 1.0f); }
 
 // Debug dump (svad_engine_set_debug_buffer): CTA 0 writes the fp32 value of every activation of its steps 0 and 1 before the
 // fp16 split, [step][region][row][slot]; tools/h16_check.py compares them with the CPU model of tools/h16_numerics.py.
@@ -382,6 +391,12 @@ __device__ __forceinline__ void run_mb(const Ctx& c, long nsteps) {
         tc_after();
 #pragma unroll 1
         for (int kc = 0; kc < 4; kc++) {
+#if !defined(SVAD_H16_NO_LSTM_HOLD)
+            // The front loop is the critical path and its STFT (6 k cycles of tensor time) would otherwise share the pipe with this LSTM.
+            // The x half (W_ih . e3) runs right away, under the front loop's window staging, when the pipe is idle; the h half (W_hh . h)
+            // waits until the STFT of the NEXT step has completed and streams under the front loop's |X| epilogue.
+            if (kc == 2 && s + 1 < nsteps) { mbar_wait(c.bar(kStftAcc), par ^ 1u); tc_after(); }
+#endif
             const uint32_t xrows = (kc < 2 ? e3_hi : h_hi) + (uint32_t)((kc & 1) * 4096);
             const uint64_t bhl = desc_b(c.sm32 + xrows, 8192);
 #pragma unroll 1
@@ -801,11 +816,11 @@ __device__ __forceinline__ void run_eb(const Ctx& c, const TileArgs& a, int firs
                 dump16(a, s, kDumpGates + 2 * 4096, j, hf, gg, d_l); dump16(a, s, kDumpGates + 3 * 4096, j, hf, go, d_l);
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const float ig = sigmoid_fast(fmaf(gi[i], d_l, bi)), fg = sigmoid_fast(fmaf(gf[i], d_l, bf));
-                    const float g2 = tanh_fast(fmaf(gg[i], d_l, bg)), og = sigmoid_fast(fmaf(go[i], d_l, bo));
+                    const float ig = sigmoid_mufu(fmaf(gi[i], d_l, bi)), fg = sigmoid_mufu(fmaf(gf[i], d_l, bf));
+                    const float g2 = tanh_mufu(fmaf(gg[i], d_l, bg)), og = sigmoid_mufu(fmaf(go[i], d_l, bo));
                     const float cn = fmaf(fg, creg[16 * hf + i], ig * g2);
                     creg[16 * hf + i] = cn;
-                    const float hn = og * tanh_fast(cn);
+                    const float hn = og * tanh_mufu(cn);
                     hreg[16 * hf + i] = hn;
                     q[i] = hn * kSh;
                 }
@@ -903,6 +918,7 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
         c.stamps = a.dbg + (2 * h16::kDumpStep * 4 + 7) / 8;   // after the two activation dumps (floats), 8-byte aligned
         c.stamp_step = nsteps / 2;
     }
+    const long long cta_t0 = clock64();   // whole-CTA spans (every CTA): implied SM clock = span / kernel time, spread = slowest / fastest
     if (warp < 4) run_ef<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
     else if (warp < 8) run_eb<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
     else if (warp == 8) run_mf<SR16>(c, nsteps);
@@ -911,6 +927,7 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
     else run_stream(c, tapeB, nsteps, G::nslabB, kH16SlabB, kH16StagesB, M::BR, kBFull0, kBEmpty0);
     tc_before();
     __syncthreads();
+    if (a.dbg && threadIdx.x == 0) (a.dbg + (2 * h16::kDumpStep * 4 + 7) / 8)[64 + blockIdx.x] = clock64() - cta_t0;
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(512u) : "memory");
 }
 

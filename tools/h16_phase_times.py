@@ -31,7 +31,7 @@ def main():
     m.engine.set_kernel("h16")
     m.engine.set_small_batch_max(0)
     x = torch.randn(B, n * T, device="cuda") * 0.03
-    nfl = 2 * STEP + 2 + 64 * 2 + 16
+    nfl = 2 * STEP + 2 + (64 + 160) * 2 + 16
     dbg = torch.zeros(nfl, device="cuda")
     L = _cabi.lib()
     L.svad_engine_set_debug_buffer.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -53,11 +53,17 @@ def main():
                 continue
             print(f"   {name:32s} t = {v - t0:8d}   (+{0 if prev is None else v - prev})")
             prev = v
-    print("per-role loop period is not visible here; kernel time / steps:")
+    spans = raw[off + 64 * 8: off + (64 + 148) * 8].view(np.int64)
+    spans = spans[spans > 0]
+    span = int(spans.max())
+    print(f"CTA spans (own clocks): min {spans.min()} median {int(np.median(spans))} max {span} cycles over {len(spans)} CTAs; "
+          f"slowest = {span / T:.0f} cycles per step")
+    print("kernel time / steps:")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); m.audio_forward_device(x, sr); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"   {ms:.3f} ms per launch = {ms * 1e-3 / T * 1.965e9:.0f} cycles per step at 1965 MHz; {B * T / ms * 1e3:.4e} chunks/s")
+    print(f"   {ms:.3f} ms per launch = {ms * 1e-3 / T * 1.965e9:.0f} cycles per step at 1965 MHz; {B * T / ms * 1e3:.4e} chunks/s; "
+          f"implied SM clock of CTA 0 = {span / (ms * 1e-3) / 1e6:.0f} MHz")
 
 
 if __name__ == "__main__":
