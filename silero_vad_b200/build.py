@@ -50,12 +50,24 @@ def build_debug():
     return dbg
 
 
+def build_variant(tag, defines):
+    """Experiment library lib/libsilero_vad_b200_<tag>.so with extra -D flags (A/B runs of kernel variants on one GPU box);
+    SVAD_DEBUG_LIB=<tag> makes the bring-up tools load it."""
+    out = LIB.with_name("libsilero_vad_b200_%s.so" % tag)
+    r = subprocess.run([nvcc_path(), *NVCC_FLAGS, *defines, "-o", str(out), *map(str, SOURCES)], capture_output=True, text=True)
+    if r.returncode:
+        print(r.stdout, r.stderr)
+        raise RuntimeError("nvcc failed building %s" % out)
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile if missing or built from other sources. Returns the library path."""
-    if os.environ.get("SVAD_DEBUG_LIB") == "1":
-        dbg = LIB.with_name("libsilero_vad_b200_dbg.so")
+    tag = os.environ.get("SVAD_DEBUG_LIB")
+    if tag:
+        dbg = LIB.with_name("libsilero_vad_b200_%s.so" % ("dbg" if tag == "1" else tag))
         if not dbg.exists():
-            raise RuntimeError("debug library missing: run silero_vad_b200.build.build_debug() first")
+            raise RuntimeError("debug library missing: run silero_vad_b200.build.build_debug() / build_variant() first")
         return dbg
     if force or stale():
         LIB.parent.mkdir(exist_ok=True)

@@ -93,6 +93,7 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
     __syncwarp();
 }
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // one epilogue group
+__device__ __forceinline__ void ef_sync() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kH16EfWarps) : "memory"); }   // all front-epilogue warps
 
 // ---------------------------------------------------------------- descriptors / MMA issue (one thread)
 __device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -443,18 +444,35 @@ __device__ __forceinline__ void stage_store(const Ctx& c, int blk, int lane, con
 // rows are whole 16-byte chunks of activation rows.  A quarter of the load instructions of the scalar variant, which was
 // instruction-bound (address arithmetic), not latency-bound.  The four row stores are issued in an order that depends on the
 // parity of rg so that one store instruction covers both halves of the 128-byte bank lines (4 wavefronts instead of 8).
+// Every audio byte is read exactly once: no L1 allocation (SVAD_H16_LDMODE 1; 0 = plain ld.global.nc -- no measurable difference).
+// The window is the one thing this kernel reads through the LSU, and it arrives slowly behind the weight streams (TMA, ~80 % of the
+// L2's throughput): 16 kHz runs at 2.23e8 chunks/s with these loads and 2.52e8 with them stubbed out (SVAD_H16_NOLOAD).  Issuing a
+// step's loads in one early burst (more registers: SVAD_H16_REGSPLIT, SVAD_H16_EF_WARPS=8) made it worse, not better -- 1.97e8 / 1.66e8:
+// the back loop's weight stream slows down when many loads are in flight -- so two blocks per warp are kept in flight, round-robin.
+#ifndef SVAD_H16_LDMODE
+#define SVAD_H16_LDMODE 1
+#endif
 __device__ __forceinline__ void ld4(const float* p, float (&x)[4]) {
+#if SVAD_H16_LDMODE == 1
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "l"(p));
+#else
     const float4 v = __ldg(reinterpret_cast<const float4*>(p));
     x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+#endif
 }
 __device__ __forceinline__ void ld4(const int16_t* p, float (&x)[4]) {
+#if SVAD_H16_LDMODE == 1
+    uint2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+#else
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+#endif
     x[0] = (float)(int16_t)(v.x & 0xffffu) * (1.0f / 32768.0f); x[1] = (float)(int16_t)(v.x >> 16) * (1.0f / 32768.0f);
     x[2] = (float)(int16_t)(v.y & 0xffffu) * (1.0f / 32768.0f); x[3] = (float)(int16_t)(v.y >> 16) * (1.0f / 32768.0f);
 }
 template <typename S>
 __device__ __forceinline__ void stagev_load(const S* p0, long ld, int nvalid, int blk, int lane, float (&v)[8][4]) {
-    const int rg = lane & 7, cg = lane >> 3;
+    const int rg = ((lane >> 2) & 1) | ((lane >> 3) << 1), cg = lane & 3;   // see stagev_store for the lane map
     const S* p = p0 + 32 * blk + 4 * rg + (long)(8 * cg) * ld;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -466,7 +484,10 @@ __device__ __forceinline__ void stagev_load(const S* p0, long ld, int nvalid, in
 template <bool SR16>
 __device__ __forceinline__ void stagev_store(const Ctx& c, int blk, int lane, const float (&v)[8][4]) {
     using G = H16Geo<SR16>;
-    const int rg = lane & 7, cg = lane >> 3;
+    // A 16-byte shared store is served a quarter warp (8 consecutive lanes) at a time, so those 8 lanes must hit the 8 different 16-byte
+    // columns of a 128-byte bank line: 4 slot groups (cg) x 2 row parities.  With lane = (rg, cg) in the natural order every quarter
+    // landed on two columns (16 wavefronts per store instead of 4, ncu round 2).
+    const int rg = ((lane >> 2) & 1) | ((lane >> 3) << 1), cg = lane & 3;
     unsigned char* hi = c.sm + H16Map::R;
     const bool odd = rg & 1;
 #pragma unroll
@@ -490,8 +511,8 @@ template <bool SR16>
 __device__ __forceinline__ void stage_reflect(const Ctx& c, int tid) {
     using G = H16Geo<SR16>;
 #pragma unroll 1
-    for (int idx = tid; idx < (G::N / 4) * 8; idx += 128) {
-        const int arr = idx & 1, ch = (idx >> 1) & 3, i = idx >> 3;
+    for (int idx = tid; idx < (G::N / 4) * 8; idx += 32 * kH16EfWarps) {
+        const int ch = idx & 3, arr = (idx >> 3) & 1, i = ((idx >> 4) << 1) | ((idx >> 2) & 1);   // a quarter warp = 4 chunks x 2 adjacent rows
         const int src = G::L1 - 2 - i, dst = G::L1 + i;
         unsigned char* base = c.sm + H16Map::R + arr * (G::XR * 64);
         *reinterpret_cast<uint4*>(base + dst * 64 + ((ch ^ ((dst >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(base + src * 64 + ((ch ^ ((src >> 1) & 3)) << 4));
@@ -505,7 +526,7 @@ __device__ __noinline__ void stage_generic(const Ctx& c, const TileArgs& a, cons
     unsigned char* hi = c.sm + H16Map::R;
     unsigned char* lo = c.sm + H16Map::R + G::XR * 64;
 #pragma unroll 1
-    for (int blk = warp; blk < G::XR / 32; blk += 4) {
+    for (int blk = warp; blk < G::XR / 32; blk += kH16EfWarps) {
         const int m = 32 * blk + lane;
 #pragma unroll 1
         for (int hf = 0; hf < 2; hf++) {
@@ -524,7 +545,13 @@ template <bool SR16, typename S>
 __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int first_tile, int tile_stride, int ntiles, int bt) {
     using G = H16Geo<SR16>;
     using M = H16Map;
-    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);   // warp 0..3 = TMEM lane quarter
+    constexpr int EW = kH16EfWarps;
+    const int wid = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    const int warp = wid & 3;                   // TMEM lane quarter (warps 0-3 and, with two groups, 12-15)
+    const int half = wid >= 12 ? 1 : 0;         // second group: frames 2, 3
+    const int w8 = warp + 4 * half;             // index among the front-epilogue warps (staging)
+    const int etid = 32 * w8 + lane;
+    const int f_lo = EW == 8 ? 2 * half : 0, f_hi = EW == 8 ? f_lo + 2 : 4;
     const S* audio = static_cast<const S*>(a.audio);
     const float* cs = a.consts;   // global; everything needed is read into registers here
     float* nyq = c.scratch() + M::s_nyq;
@@ -536,6 +563,7 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
     const int o = 32 * warp + lane;                                      // enc0 output channel
     const float b0 = cs[M::c_b0 + o], wn0 = cs[M::c_wnyq + o], wn1 = cs[M::c_wnyq + 128 + o], wn2 = cs[M::c_wnyq + 256 + o];
     const bool vec_ok = (a.ld % 4 == 0) && (reinterpret_cast<uintptr_t>(audio) % (4 * sizeof(S)) == 0);   // rows start on 4-sample boundaries
+    const bool ctx_vec_ok = !a.ctx_in || ((a.ctx_ld % 4 == 0) && (reinterpret_cast<uintptr_t>(a.ctx_in) % 16 == 0));
     long s = 0;
     for (int tile = first_tile; tile < ntiles; tile += tile_stride) {
         const int g0 = tile * bt;
@@ -543,57 +571,100 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
             const uint32_t par = (uint32_t)(s & 1);
             // ---- stage the window of chunk t (the front region is free once enc1 of the previous step has completed)
             SVAD_H16_STAMP(0, 0);
-            const bool fast = (t > 0) && ((t + 1) * G::n <= a.L) && a.dec == 1;
-            float va[8][4], vb[8][4];
+            // the first chunk of a row takes its context blocks from the carried-in context (or zeros) instead of the row
+            const bool fast = ((t + 1) * G::n <= a.L) && a.dec == 1 && (t > 0 || (vec_ok && ctx_vec_ok));
+            constexpr int NBV = G::L1 / 32;        // 18 / 9 blocks of [context | chunk]; the reflect rows are copied afterwards
+            constexpr int KBV = (NBV + EW - 1) / EW;   // blocks per warp (warp w takes w, w + EW, ...)
+#ifndef SVAD_H16_EARLY
+#if SVAD_H16_EF_WARPS == 8 || defined(SVAD_H16_REGSPLIT)
+#define SVAD_H16_EARLY KBV
+#else
+#define SVAD_H16_EARLY 2   // 168 registers per thread: two blocks in flight across the wait, the rest loaded after it
+#endif
+#endif
+            float v[SVAD_H16_EARLY][8][4];
             const S* p0 = audio + (long)g0 * a.ld + (t * G::n - G::ctx);
             const int nvalid = (a.B - g0 < bt) ? a.B - g0 : bt;
-            // the first two blocks of this warp are loaded while enc1 of the previous step still owns the front region
+            // every block of this warp is loaded (into registers) while enc1 of the previous step still owns the front region
+            auto load_block = [&](int blk, float (&vk)[8][4]) {
+#ifdef SVAD_H16_NOLOAD   // experiment: no audio loads at all (what do the window stores cost alone?)
+#pragma unroll
+                for (int j = 0; j < 8; j++) { vk[j][0] = 0.01f * (float)blk; vk[j][1] = 0.02f; vk[j][2] = -0.01f * (float)lane; vk[j][3] = 0.005f; }
+                return;
+#endif
+                if (t == 0 && blk < G::ctx / 32) {
+                    if (a.ctx_in) {
+                        stagev_load<float>(a.ctx_in + (long)g0 * a.ctx_ld, a.ctx_ld, nvalid, blk, lane, vk);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { vk[j][0] = 0.0f; vk[j][1] = 0.0f; vk[j][2] = 0.0f; vk[j][3] = 0.0f; }
+                    }
+                } else {
+                    stagev_load<S>(p0, a.ld, nvalid, blk, lane, vk);
+                }
+            };
             if (fast && vec_ok) {
-                stagev_load<S>(p0, a.ld, nvalid, warp, lane, va);
-                stagev_load<S>(p0, a.ld, nvalid, warp + 4, lane, vb);
+#pragma unroll
+                for (int k = 0; k < KBV; k++)
+                    if (k < SVAD_H16_EARLY && w8 + EW * k < NBV) load_block(w8 + EW * k, v[k % SVAD_H16_EARLY]);
             }
             if (s > 0) mbar_wait(c.bar(kFDone), par ^ 1u);
             SVAD_H16_STAMP(0, 1);
             {
                 if (t + 1 < a.T && a.dec == 1) {   // pull the next chunk of every stream of the tile into L2
-                    constexpr int kPerLine = 128 / (int)sizeof(S), kLines = G::n / kPerLine;
+#ifndef SVAD_H16_PREFETCH   // 0: one prefetch.global.L2 per 128-byte line (default), 1: per 64 bytes, 2: one cp.async.bulk.prefetch.L2 per stream
+#define SVAD_H16_PREFETCH 0   // measured 16 kHz / 8 kHz: 2.232e8 / 2.881e8, 2.209e8 / 2.926e8, 2.18e8 / 2.83e8 chunks/s
+#endif
+                    const long off = (t + 1) * G::n;
+#if SVAD_H16_PREFETCH == 2
+                    // one bulk prefetch per stream
+                    if (vec_ok && (a.ld * sizeof(S)) % 16 == 0) {
+                        if (etid < bt && g0 + etid < a.B && off < a.L) {
+                            const long cnt = (a.L - off < G::n) ? a.L - off : (long)G::n;
+                            const uint32_t bytes = (uint32_t)(cnt * sizeof(S)) & ~15u;
+                            if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(audio + (long)(g0 + etid) * a.ld + off), "r"(bytes) : "memory");
+                        }
+                    } else
+#endif
+                    {
+                        constexpr int kPerLine = (SVAD_H16_PREFETCH == 1 ? 64 : 128) / (int)sizeof(S), kLines = G::n / kPerLine;
 #pragma unroll 1
-                    for (int i = (int)threadIdx.x; i < bt * kLines; i += 128) {
-                        const int loc = i / kLines, line = i % kLines, g = g0 + loc;
-                        const long off = (t + 1) * G::n + line * kPerLine;
-                        if (g < a.B && off < a.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(audio + (long)g * a.ld + off));
+                        for (int i = etid; i < bt * kLines; i += 32 * EW) {
+                            const int loc = i / kLines, line = i % kLines, g = g0 + loc;
+                            const long o2 = off + line * kPerLine;
+                            if (g < a.B && o2 < a.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(audio + (long)g * a.ld + o2));
+                        }
                     }
                 }
                 if (fast && vec_ok) {
-                    constexpr int NB = G::L1 / 32;   // 18 / 9 blocks of [context | chunk] (every warp has >= 2); the reflect rows are copied afterwards
-#pragma unroll 1
-                    for (int blk = warp; blk < NB; blk += 8) {
-                        stagev_store<SR16>(c, blk, lane, va);
-                        if (blk + 8 < NB) stagev_load<S>(p0, a.ld, nvalid, blk + 8, lane, va);
-                        if (blk + 4 < NB) {
-                            stagev_store<SR16>(c, blk + 4, lane, vb);
-                            if (blk + 12 < NB) stagev_load<S>(p0, a.ld, nvalid, blk + 12, lane, vb);
-                        }
+                    // blocks beyond the early ones reuse the register buffers round-robin: store block k, then load block k + EARLY into it
+#pragma unroll
+                    for (int k = 0; k < KBV; k++) {
+                        if (w8 + EW * k < NBV) stagev_store<SR16>(c, w8 + EW * k, lane, v[k % SVAD_H16_EARLY]);
+                        if (k + SVAD_H16_EARLY < KBV && w8 + EW * (k + SVAD_H16_EARLY) < NBV) load_block(w8 + EW * (k + SVAD_H16_EARLY), v[k % SVAD_H16_EARLY]);
                     }
-                    group_sync(2);
-                    stage_reflect<SR16>(c, (int)threadIdx.x);
+                    SVAD_H16_STAMP(0, 7);
+                    ef_sync();
+                    SVAD_H16_STAMP(0, 8);
+                    stage_reflect<SR16>(c, etid);
+                    SVAD_H16_STAMP(0, 9);
                 } else if (fast) {
                     constexpr int NB = G::XR / 32;   // 20 / 10 blocks, warp w takes w, w + 4, ...
                     const S* p0 = audio + (long)g0 * a.ld + (t * G::n - G::ctx);
                     const int nvalid = (a.B - g0 < bt) ? a.B - g0 : bt;
                     float va[32], vb[32];
-                    stage_load<SR16, S>(p0, a.ld, nvalid, warp, lane, va);
+                    stage_load<SR16, S>(p0, a.ld, nvalid, w8, lane, va);
 #pragma unroll 1
-                    for (int blk = warp; blk < NB; blk += 8) {
-                        if (blk + 4 < NB) stage_load<SR16, S>(p0, a.ld, nvalid, blk + 4, lane, vb);
+                    for (int blk = w8; blk < NB; blk += 2 * EW) {
+                        if (blk + EW < NB) stage_load<SR16, S>(p0, a.ld, nvalid, blk + EW, lane, vb);
                         stage_store<SR16>(c, blk, lane, va);
-                        if (blk + 4 < NB) {
-                            if (blk + 8 < NB) stage_load<SR16, S>(p0, a.ld, nvalid, blk + 8, lane, va);
-                            stage_store<SR16>(c, blk + 4, lane, vb);
+                        if (blk + EW < NB) {
+                            if (blk + 2 * EW < NB) stage_load<SR16, S>(p0, a.ld, nvalid, blk + 2 * EW, lane, va);
+                            stage_store<SR16>(c, blk + EW, lane, vb);
                         }
                     }
                 } else {
-                    stage_generic<SR16, S>(c, a, audio, g0, bt, t, warp, lane);
+                    stage_generic<SR16, S>(c, a, audio, g0, bt, t, w8, lane);
                 }
             }
             fence_async();
@@ -608,7 +679,7 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
                 unsigned char* hi = c.sm + M::R;
                 unsigned char* lo = c.sm + M::R + 4 * G::Kt * 64;
 #pragma unroll 1
-                for (int f = 0; f < 4; f++) {
+                for (int f = f_lo; f < f_hi; f++) {
                     float re[2][16], im[2][16];
                     tmem_ld16(tq + (uint32_t)(f * 32), re[0]);
                     tmem_ld16(tq + (uint32_t)(f * 32 + 16), re[1]);
@@ -645,7 +716,7 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
                 unsigned char* hi = c.sm + M::R;
                 unsigned char* lo = c.sm + M::R + 32768;
 #pragma unroll 1
-                for (int tt = 0; tt < 4; tt++) {
+                for (int tt = f_lo; tt < f_hi; tt++) {
                     float vv[2][16];
                     tmem_ld16(tq + (uint32_t)(tt * 32), vv[0]);
                     tmem_ld16(tq + (uint32_t)(tt * 32 + 16), vv[1]);
@@ -839,7 +910,7 @@ __device__ __forceinline__ void run_eb(const Ctx& c, const TileArgs& a, int firs
                 float acc = 0.0f;
 #pragma unroll 8
                 for (int u = 0; u < 32; u++) {
-                    const int r = 32 * part + u;
+                    const int r = 4 * u + part;   // the four parts read adjacent rows: different bank groups (rows 32 apart share banks)
                     const int pos = r * 32 + ((((sl >> 3) ^ ((r >> 1) & 3)) << 3) | (sl & 7));
                     const float hv = (__half2float(hh[pos]) + __half2float(hl[pos])) * (1.0f / kSh);
                     acc = fmaf(wout[r], relu_f(hv), acc);
@@ -897,8 +968,8 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
     if (threadIdx.x == 0) {
         for (int b = 0; b < kNumBars; b++) {
             // group barriers: one arrival per warp of the 4-warp epilogue group; commit / TMA barriers: one arrival
-            const bool grp = (b == kXpFull || b == kMagFull || b == kE0Full || b == kE1Ready || b == kE2Full || b == kE3Full);
-            mbar_init(c.bar(b), grp ? 4u : 1u);
+            const bool grp_f = (b == kXpFull || b == kMagFull || b == kE0Full), grp_b = (b == kE1Ready || b == kE2Full || b == kE3Full);
+            mbar_init(c.bar(b), grp_f ? (uint32_t)kH16EfWarps : grp_b ? 4u : 1u);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async();
@@ -919,12 +990,33 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
         c.stamp_step = nsteps / 2;
     }
     const long long cta_t0 = clock64();   // whole-CTA spans (every CTA): implied SM clock = span / kernel time, spread = slowest / fastest
-    if (warp < 4) run_ef<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
-    else if (warp < 8) run_eb<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
-    else if (warp == 8) run_mf<SR16>(c, nsteps);
-    else if (warp == 9) run_mb(c, nsteps);
-    else if (warp == 10) run_stream(c, tapeF, nsteps, G::nslabF, kH16SlabF, kH16StagesF, M::FR, kFFull0, kFEmpty0);
-    else run_stream(c, tapeB, nsteps, G::nslabB, kH16SlabB, kH16StagesB, M::BR, kBFull0, kBEmpty0);
+    // Register file split by warpgroup (setmaxnreg works on 4 aligned warps).  Two front groups (512 threads, compiled for 128 registers):
+    // the issue / stream warps give back 88 each, the back epilogue (cell + hidden state of 32 slots in registers) takes 72, the front
+    // groups 8: 136 + 200 + 40 + 136 = 4 * 128.  One front group (384 threads x 168): optional 232 + 232 + 40 (SVAD_H16_REGSPLIT).
+    // (each setmaxnreg sits at the head of its role's branch: ptxas allocates the code it dominates against that limit)
+#if SVAD_H16_EF_WARPS == 8
+    constexpr int kRegEf = 136, kRegEb = 200, kRegRole = 40;
+    constexpr bool kRegSplit = true;
+#elif defined(SVAD_H16_REGSPLIT)
+    constexpr int kRegEf = 232, kRegEb = 232, kRegRole = 40;
+    constexpr bool kRegSplit = true;
+#else
+    constexpr int kRegEf = 0, kRegEb = 0, kRegRole = 0;
+    constexpr bool kRegSplit = false;
+#endif
+    if (warp < 4 || warp >= 12) {
+        if (kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegSplit ? kRegEf : 24));
+        run_ef<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
+    } else if (warp < 8) {
+        if (kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegSplit ? kRegEb : 24));
+        run_eb<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
+    } else {
+        if (kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegSplit ? kRegRole : 24));
+        if (warp == 8) run_mf<SR16>(c, nsteps);
+        else if (warp == 9) run_mb(c, nsteps);
+        else if (warp == 10) run_stream(c, tapeF, nsteps, G::nslabF, kH16SlabF, kH16StagesF, M::FR, kFFull0, kFEmpty0);
+        else run_stream(c, tapeB, nsteps, G::nslabB, kH16SlabB, kH16StagesB, M::BR, kBFull0, kBEmpty0);
+    }
     tc_before();
     __syncthreads();
     if (a.dbg && threadIdx.x == 0) (a.dbg + (2 * h16::kDumpStep * 4 + 7) / 8)[64 + blockIdx.x] = clock64() - cta_t0;

@@ -52,7 +52,14 @@ struct H16Geo {
 // 78-96 B/clk/SM, ceiling ~105-110): the back tape, dominated by the LSTM's 512 KB per step, moves in 32 KB slabs.
 constexpr int kH16SlabF = 16384, kH16SlabB = 32768;
 constexpr int kH16StagesF = 3, kH16StagesB = 2;
-constexpr int kH16Threads = 384;   // warps 0-3 front epilogue, 4-7 back epilogue, 8 / 9 MMA issue (front / back), 10 / 11 weight streams
+// warps 0-3 front epilogue, 4-7 back epilogue, 8 / 9 MMA issue (front / back), 10 / 11 weight streams; with SVAD_H16_EF_WARPS == 8 a second
+// front-epilogue group (warps 12-15) takes frames 2, 3 of the |X| / enc0 epilogues and every other block of the window staging
+#ifndef SVAD_H16_EF_WARPS
+#define SVAD_H16_EF_WARPS 4
+#endif
+constexpr int kH16EfWarps = SVAD_H16_EF_WARPS;
+static_assert(kH16EfWarps == 4 || kH16EfWarps == 8, "front epilogue: one or two groups of four warps");
+constexpr int kH16Threads = 384 + 32 * (kH16EfWarps - 4);
 
 // activation scales (exact powers of two).  |x| <= 1 for normalised audio; mag <= 181 |x|; e0..e3 were observed <= 72 on speech
 // at amplitude 0.55 (tools/h16_numerics.py) -- the conversions saturate at 65504, far above anything normalised audio produces.

@@ -14,7 +14,8 @@ from silero_vad_b200 import _cabi, load_silero_vad  # noqa: E402
 
 STEP = 4 * 128 * 32 + 128 + 4 * 128 * 32 + 2 * 64 * 32 + 64 * 32 + 128 * 32 + 4 * 128 * 32 + 128 * 32 + 128 * 32
 NAMES = {
-    0: ["loop top", "front region free (f_done)", "window staged", "STFT acc ready", "mag written", "enc0 acc ready", "e0 written"],
+    0: ["loop top", "front region free (f_done)", "window staged", "STFT acc ready", "mag written", "enc0 acc ready", "e0 written",
+        "  (window rows stored)", "  (group sync)", "  (reflect rows copied)"],
     1: ["loop top", "xp ready", "enc1 acc drained", "STFT issued", "mag ready", "enc0 issued", "e0 ready", "enc1 issued"],
     2: ["loop top", "f_done", "e1 written", "enc2 acc", "e2 written", "enc3 acc", "e3 written", "LSTM acc", "h written+sync", "head done"],
     3: ["loop top", "e1 ready", "enc2 issued", "e2 ready", "enc3 issued", "e3 ready", "LSTM issued"],
@@ -47,8 +48,7 @@ def main():
     for r in range(4):
         print(ROLE[r])
         prev = None
-        for k, name in enumerate(NAMES[r]):
-            v = int(st[r][k])
+        for v, name in sorted((int(st[r][k]), name) for k, name in enumerate(NAMES[r])):
             if not v:
                 continue
             print(f"   {name:32s} t = {v - t0:8d}   (+{0 if prev is None else v - prev})")
@@ -60,8 +60,11 @@ def main():
           f"slowest = {span / T:.0f} cycles per step")
     print("kernel time / steps:")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); m.audio_forward_device(x, sr); e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    e0.record()
+    for _ in range(10):
+        m.audio_forward_device(x, sr)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
     print(f"   {ms:.3f} ms per launch = {ms * 1e-3 / T * 1.965e9:.0f} cycles per step at 1965 MHz; {B * T / ms * 1e3:.4e} chunks/s; "
           f"implied SM clock of CTA 0 = {span / (ms * 1e-3) / 1e6:.0f} MHz")
 
