@@ -56,6 +56,11 @@ int svad_engine_set_kernel(svad_engine* e, int kernel);
 /* Batches of up to `streams` streams run on the small-batch cluster kernel (8-CTA clusters with the network split
  * across their shared memories; the latency path).  Default 256 (measured crossover with the tile kernels); 0 disables it. */
 int svad_engine_set_small_batch_max(svad_engine* e, int streams);
+/* svad_fused_h16 in CTA pairs (thread-block clusters of 2): each CTA of a pair fetches half of every weight slab and multicasts it
+ * into both shared memories, which halves the bytes the kernel reads out of L2 (same probabilities, bit for bit).  Default on for
+ * batches of >= 64 streams (environment SVAD_H16_PAIR=0 turns the default off); falls back to single CTAs when the device cannot
+ * co-schedule pairs. */
+int svad_engine_set_pair_mode(svad_engine* e, int on);
 /* Number of SMs of the engine's device. */
 int svad_engine_sm_count(const svad_engine* e);
 /* Kernel launches issued by this engine so far (bench.py's gpu_launches). */

@@ -11,7 +11,7 @@ _f32p = ctypes.c_void_p  # device or host float* passed as an integer address
 _lib = None
 
 EXPORTS = ["svad_abi_version", "svad_last_error", "svad_engine_create", "svad_engine_destroy",
-           "svad_engine_set_tile_rows", "svad_engine_set_kernel", "svad_engine_set_small_batch_max", "svad_engine_sm_count", "svad_engine_launch_count",
+           "svad_engine_set_tile_rows", "svad_engine_set_kernel", "svad_engine_set_small_batch_max", "svad_engine_set_pair_mode", "svad_engine_sm_count", "svad_engine_launch_count",
            "svad_forward_device", "svad_forward_device_pcm16", "svad_forward_device_ex", "svad_step_device", "svad_forward_host",
            "svad_collect_chunks_device", "svad_stream_open", "svad_stream_push", "svad_stream_reset", "svad_stream_close",
            "svad_forward_host_pcm16", "svad_step_host",
@@ -48,6 +48,7 @@ def lib():
     L.svad_engine_set_tile_rows.argtypes = [vp, i32]
     L.svad_engine_set_kernel.argtypes = [vp, i32]
     L.svad_engine_set_small_batch_max.argtypes = [vp, i32]
+    L.svad_engine_set_pair_mode.argtypes = [vp, i32]
     L.svad_engine_sm_count.argtypes = [vp]
     L.svad_engine_launch_count.argtypes = [vp]
     L.svad_engine_launch_count.restype = i64
@@ -106,6 +107,9 @@ class Engine:
     def set_kernel(self, kernel):
         """0 / 'fp32' = CUDA-core kernel, 1 / 'tc' = tcgen05 split-TF32 kernel, 2 / 'h16' = tcgen05 split-fp16 two-loop kernel."""
         check(lib().svad_engine_set_kernel(self._h, {"fp32": 0, "tc": 1, "h16": 2}.get(kernel, kernel)))
+
+    def set_pair_mode(self, on):
+        check(lib().svad_engine_set_pair_mode(self._h, 1 if on else 0))
 
     def set_small_batch_max(self, streams):
         check(lib().svad_engine_set_small_batch_max(self._h, streams))

@@ -687,6 +687,7 @@ struct svad_engine {
     float* d_h16_c[2] = {nullptr, nullptr};
     float* d_small[2] = {nullptr, nullptr};    // small-batch cluster kernel: 8 per-CTA weight slices
     int small_max = 256;                       // streams up to which the cluster kernel is used (0 = never); crossover with the tile kernels measured at ~256
+    int h16_pair = getenv("SVAD_H16_PAIR") ? atoi(getenv("SVAD_H16_PAIR")) : 1;   // svad_fused_h16 in CTA pairs sharing the weight streams
     int kernel = 2;                            // 0 = fp32 CUDA cores, 1 = tcgen05 split-TF32, 2 = tcgen05 split-fp16 two-loop kernel (default)
     long long* dbg = nullptr;
     int64_t launches = 0;
@@ -803,6 +804,12 @@ extern "C" int svad_engine_set_debug_buffer(svad_engine* e, long long* d_buf) {
     e->dbg = d_buf;
     return SVAD_OK;
 }
+extern "C" int svad_engine_set_pair_mode(svad_engine* e, int on) {
+    if (!e) return fail(SVAD_EINVAL, "null engine");
+    e->h16_pair = on ? 1 : 0;
+    return SVAD_OK;
+}
+
 extern "C" int svad_engine_set_small_batch_max(svad_engine* e, int streams) {
     if (!e || streams < 0) return fail(SVAD_EINVAL, "small-batch limit must be >= 0");
     e->small_max = streams;
@@ -867,10 +874,11 @@ static int launch_small(svad_engine* e, const TileArgs& a, cudaStream_t st) {
 }
 
 // fp16 split kernel: streams per tile chosen so that the tiles fill whole waves of SMs (B = 4096 on 148 SMs: 147 tiles of 28).
-static int pick_bt(const svad_engine* e, int B) {
+static int pick_bt(const svad_engine* e, int B, int sms = 0) {
     if (e->tile_rows) return 4 * e->tile_rows;
-    const long tiles32 = (B + 31) / 32, waves = (tiles32 + e->sms - 1) / e->sms;
-    const long target = waves * e->sms;
+    if (sms <= 0) sms = e->sms;
+    const long tiles32 = (B + 31) / 32, waves = (tiles32 + sms - 1) / sms;
+    const long target = waves * sms;
     long bt = (B + target - 1) / target;
     return (int)(bt < 1 ? 1 : (bt > 32 ? 32 : bt));
 }
@@ -883,10 +891,45 @@ static int launch_h16(svad_engine* e, const TileArgs& a, cudaStream_t st) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H16Map::total));
         configured[e->device & 15] = true;
     }
+    const int br = SR16 ? 0 : 1;
+    if (e->h16_pair && a.B >= 64) {
+        // CTA pairs (clusters of 2) share the weight streams: each CTA fetches half of every slab and multicasts it to both, which halves
+        // the bytes read out of L2.  Both CTAs of a pair must walk the same number of tiles, so every CTA gets ceil(ntiles / grid) of
+        // them; the surplus ones lie past the batch (every load and store of such a tile is masked).
+        auto kp = svad_fused_h16<SR16, S, true>;
+        static bool configured_p[16] = {};
+        static int pairs[16] = {};
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(kH16Threads); cfg.dynamicSmemBytes = H16Map::total; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (!configured_p[e->device & 15]) {
+            CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H16Map::total));
+            cfg.gridDim = dim3(2 * (e->sms / 2));
+            int n = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kp, &cfg));
+            pairs[e->device & 15] = n;
+            configured_p[e->device & 15] = true;
+            if (getenv("SVAD_VERBOSE")) fprintf(stderr, "svad: h16 pair mode: %d co-resident CTA pairs on %d SMs\n", n, e->sms);
+        }
+        const int np = pairs[e->device & 15];
+        if (np >= 1) {
+            const int bt = pick_bt(e, a.B, 2 * np);
+            const int ntiles = (a.B + bt - 1) / bt;
+            int grid = ((ntiles + 1) / 2) * 2;
+            if (grid > 2 * np) grid = 2 * np;
+            const int ntiles_eff = ((ntiles + grid - 1) / grid) * grid;
+            cfg.gridDim = dim3(grid);
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, kp, a, (const unsigned char*)e->d_h16_f[br], (const unsigned char*)e->d_h16_b[br], ntiles_eff, bt));
+            e->launches++;
+            return SVAD_OK;
+        }
+    }
     const int bt = pick_bt(e, a.B);
     const int ntiles = (a.B + bt - 1) / bt;
     const int grid = ntiles < e->sms ? ntiles : e->sms;
-    const int br = SR16 ? 0 : 1;
     kern<<<grid, kH16Threads, H16Map::total, st>>>(a, e->d_h16_f[br], e->d_h16_b[br], ntiles, bt);
     CUDA_TRY(cudaGetLastError());
     e->launches++;

@@ -92,6 +92,19 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
     if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     __syncwarp();
 }
+// CTA-pair mode: the two CTAs of a cluster share every weight slab (each fetches half of it and multicasts it into both shared
+// memories), so a ring stage may be refilled only when BOTH issue warps have released it: the release is committed to both CTAs.
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    if (elect_one()) {
+        const uint16_t mask = 3;
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }   // one epilogue group
 __device__ __forceinline__ void ef_sync() { asm volatile("bar.sync 2, %0;" ::"n"(32 * kH16EfWarps) : "memory"); }   // all front-epilogue warps
 
@@ -219,19 +232,27 @@ struct Ctx {
 };
 
 // ================================================================ weight streams (one thread each)
+template <bool CL>
 __device__ __forceinline__ void run_stream(const Ctx& c, const unsigned char* tape, long nsteps, int nslab, int slab_bytes, int nstages, int ring_off, int full0, int empty0) {
     const long total = nsteps * nslab;
     int idx = 0, stage = 0;
     uint32_t round = 0;   // how often the ring has wrapped
+    const uint32_t half = CL ? cluster_rank() * (uint32_t)(slab_bytes / 2) : 0u;   // pair mode: this CTA fetches its half of every slab for both
 #pragma unroll 1
     for (long i = 0; i < total; i++) {
         if (round > 0) mbar_wait_spin(c.bar(empty0 + stage), (round - 1) & 1u);
         const uint32_t bar = c.bar(full0 + stage), dst = c.sm32 + (uint32_t)(ring_off + stage * slab_bytes);
         if (elect_one()) {
-            mbar_expect_tx(bar, (uint32_t)slab_bytes);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "l"(tape + (size_t)idx * slab_bytes), "r"(slab_bytes), "r"(bar)
-                         : "memory");
+            mbar_expect_tx(bar, (uint32_t)slab_bytes);   // the whole slab: the other half arrives from the peer's copy
+            if constexpr (CL) {
+                const uint16_t mask = 3;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                             ::"r"(dst + half), "l"(tape + (size_t)idx * slab_bytes + half), "r"(slab_bytes / 2), "r"(bar), "h"(mask) : "memory");
+            } else {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                             "l"(tape + (size_t)idx * slab_bytes), "r"(slab_bytes), "r"(bar)
+                             : "memory");
+            }
         }
         __syncwarp();
         if (++idx == nslab) idx = 0;
@@ -240,7 +261,7 @@ __device__ __forceinline__ void run_stream(const Ctx& c, const unsigned char* ta
 }
 
 // ================================================================ MF: front MMA issue (one thread)
-template <bool SR16>
+template <bool SR16, bool CL>
 __device__ __forceinline__ void run_mf(const Ctx& c, long nsteps) {
     using G = H16Geo<SR16>;
     using M = H16Map;
@@ -251,7 +272,7 @@ __device__ __forceinline__ void run_mf(const Ctx& c, long nsteps) {
         return c.sm32 + (uint32_t)(M::FR + stage * kH16SlabF);
     };
     auto slab_done = [&]() {
-        tc_commit(c.bar(kFEmpty0 + stage));
+        if constexpr (CL) tc_commit_pair(c.bar(kFEmpty0 + stage)); else tc_commit(c.bar(kFEmpty0 + stage));
         if (++stage == kH16StagesF) { stage = 0; round++; }
     };
     constexpr uint32_t xp_hi = M::R, xp_lo = M::R + G::XR * 64;
@@ -340,6 +361,7 @@ __device__ __forceinline__ void run_mf(const Ctx& c, long nsteps) {
 }
 
 // ================================================================ MB: back MMA issue (one thread)
+template <bool CL>
 __device__ __forceinline__ void run_mb(const Ctx& c, long nsteps) {
     using M = H16Map;
     int stage = 0;
@@ -349,7 +371,7 @@ __device__ __forceinline__ void run_mb(const Ctx& c, long nsteps) {
         return c.sm32 + (uint32_t)(M::BR + stage * kH16SlabB);
     };
     auto slab_done = [&]() {
-        tc_commit(c.bar(kBEmpty0 + stage));
+        if constexpr (CL) tc_commit_pair(c.bar(kBEmpty0 + stage)); else tc_commit(c.bar(kBEmpty0 + stage));
         if (++stage == kH16StagesB) { stage = 0; round++; }
     };
     constexpr uint32_t e1_hi = M::P, e1_lo = M::P + 8192, e2_hi = M::P, e2_lo = M::P + 4096, e3_hi = M::P, h_hi = M::H;
@@ -950,7 +972,7 @@ __device__ __forceinline__ void run_eb(const Ctx& c, const TileArgs& a, int firs
 }  // namespace h16
 
 // ================================================================ kernel
-template <bool SR16, typename S>
+template <bool SR16, typename S, bool CL = false>
 __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, const unsigned char* tapeF, const unsigned char* tapeB, int ntiles, int bt) {
     using namespace h16;
     using G = H16Geo<SR16>;
@@ -969,7 +991,8 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
         for (int b = 0; b < kNumBars; b++) {
             // group barriers: one arrival per warp of the 4-warp epilogue group; commit / TMA barriers: one arrival
             const bool grp_f = (b == kXpFull || b == kMagFull || b == kE0Full), grp_b = (b == kE1Ready || b == kE2Full || b == kE3Full);
-            mbar_init(c.bar(b), grp_f ? (uint32_t)kH16EfWarps : grp_b ? 4u : 1u);
+            const bool ring_empty = (b >= kFEmpty0 && b < kFEmpty0 + kH16StagesF) || (b >= kBEmpty0 && b < kBEmpty0 + kH16StagesB);
+            mbar_init(c.bar(b), grp_f ? (uint32_t)kH16EfWarps : grp_b ? 4u : (CL && ring_empty) ? 2u : 1u);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async();
@@ -980,6 +1003,7 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
     }
     tc_before();
     __syncthreads();
+    if constexpr (CL) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
     tc_after();
     c.tmem = *tmem_slot;
     int my_tiles = 0;
@@ -1012,13 +1036,14 @@ __global__ void __launch_bounds__(kH16Threads, 1) svad_fused_h16(TileArgs a, con
         run_eb<SR16, S>(c, a, (int)blockIdx.x, (int)gridDim.x, ntiles, bt);
     } else {
         if (kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegSplit ? kRegRole : 24));
-        if (warp == 8) run_mf<SR16>(c, nsteps);
-        else if (warp == 9) run_mb(c, nsteps);
-        else if (warp == 10) run_stream(c, tapeF, nsteps, G::nslabF, kH16SlabF, kH16StagesF, M::FR, kFFull0, kFEmpty0);
-        else run_stream(c, tapeB, nsteps, G::nslabB, kH16SlabB, kH16StagesB, M::BR, kBFull0, kBEmpty0);
+        if (warp == 8) run_mf<SR16, CL>(c, nsteps);
+        else if (warp == 9) run_mb<CL>(c, nsteps);
+        else if (warp == 10) run_stream<CL>(c, tapeF, nsteps, G::nslabF, kH16SlabF, kH16StagesF, M::FR, kFFull0, kFEmpty0);
+        else run_stream<CL>(c, tapeB, nsteps, G::nslabB, kH16SlabB, kH16StagesB, M::BR, kBFull0, kBEmpty0);
     }
     tc_before();
     __syncthreads();
+    if constexpr (CL) cluster_sync_all();   // neither CTA leaves while the other may still signal its barriers
     if (a.dbg && threadIdx.x == 0) (a.dbg + (2 * h16::kDumpStep * 4 + 7) / 8)[64 + blockIdx.x] = clock64() - cta_t0;
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(512u) : "memory");
 }

@@ -316,3 +316,25 @@ def test_persistent_stream_session(torch_cuda, fixtures, meta, name):
         assert float(np.abs(got - want).max()) < TIGHT
     # the engine still serves ordinary calls while / after sessions
     assert float(np.abs(m.audio_forward(wav[None, : n * 50], sr).numpy()[0] - fx["probs"][:50]).max()) < TIGHT
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sr", [16000, 8000])
+def test_pair_mode_is_bit_identical(torch_cuda, sr):
+    """svad_fused_h16 in CTA pairs (weight slabs fetched half each and multicast) against the single-CTA launch: same arithmetic in the
+    same order, so the probabilities and the carried state must be identical bit for bit -- for batches whose tile count is odd
+    (a pair gets a surplus tile past the batch), for several tiles per CTA, for a ragged last tile and a ragged last chunk."""
+    torch = torch_cuda
+    n = 512 if sr == 16000 else 256
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for B, L in ((64, 5 * n), (4096, 6 * n), (4115, 3 * n + 17), (8192 + 29, 4 * n), (300, 7 * n + n // 2)):
+        x = torch.randn(B, L, device="cuda", generator=g) * 0.05
+        out = {}
+        for on in (0, 1):
+            m = make_model("h16")
+            m.engine.set_pair_mode(on)
+            p = m.audio_forward_device(x, sr)
+            st, cx = m.get_states()[:2]
+            out[on] = (p.clone(), st.clone(), cx.clone())
+        for a, b in zip(out[0], out[1]):
+            assert torch.equal(a, b), (B, L)
