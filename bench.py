@@ -534,7 +534,7 @@ def run_b200(args):
                                      "peak_source": ("measured (MEASURED_PEAKS.json bf16_tflops, burst" if "bf16_tflops" in pk else "nominal (2.25 PFLOP/s dense bf16")
                                                     + ("; fp16 runs at the bf16 rate)" if args.kernel == "h16" else "; tf32 at half of it)"),
                                      "frac_of_sustained_peak": 3.0 * algo_t / (rate * bf16_sus),
-                                     "note": "MACs on tcgen05 x 3 products of the hi/lo split; with 28 streams per SM an instruction covers 32-128 columns and costs "
+                                     "note": "MACs on tcgen05 x 3 products of the hi/lo split; with 32 streams per CTA (one CTA per SM) an instruction covers 32-128 columns and costs "
                                              "46-64 cycles (tools/umma_f16_unit.cu), i.e. 1/4 - 1/2 of the dense rate: the instruction count, not the FLOP peak, binds"}
     if e2e:
         out["e2e"] = e2e

@@ -874,13 +874,21 @@ static int launch_small(svad_engine* e, const TileArgs& a, cudaStream_t st) {
 }
 
 // fp16 split kernel: streams per tile chosen so that the tiles fill whole waves of SMs (B = 4096 on 148 SMs: 147 tiles of 28).
-static int pick_bt(const svad_engine* e, int B, int sms = 0) {
+// Streams per tile of svad_fused_h16.  A CTA's step costs the same for 1 or 32 streams (the MMAs run at N = 32 per frame and the epilogue
+// threads cover 32 slots either way), so tiles are always full: B = 4096 takes 128 CTAs, not 148 -- measured the same kernel time
+// (1.183 vs 1.172 ms), 13 % fewer weight streams out of L2, and 20 SMs left for whatever else the device runs (the asynchronous
+// all-gather of a multi-GPU job, copies).  `grid` = CTAs that walk `waves` tiles each (even for CTA pairs).
+static int pick_bt(const svad_engine* e, int B) {
     if (e->tile_rows) return 4 * e->tile_rows;
-    if (sms <= 0) sms = e->sms;
-    const long tiles32 = (B + 31) / 32, waves = (tiles32 + sms - 1) / sms;
-    const long target = waves * sms;
-    long bt = (B + target - 1) / target;
-    return (int)(bt < 1 ? 1 : (bt > 32 ? 32 : bt));
+    return B < 32 ? (B < 1 ? 1 : B) : 32;
+}
+static void pick_grid(int ntiles, int sms, bool pairs, int* grid, int* ntiles_eff) {
+    const int waves = (ntiles + sms - 1) / sms;
+    int g = (ntiles + waves - 1) / waves;
+    if (pairs) g = ((g + 1) / 2) * 2;
+    if (g > sms) g = sms;
+    *grid = g;
+    *ntiles_eff = pairs ? ((ntiles + g - 1) / g) * g : ntiles;   // a pair walks the same number of tiles (surplus ones lie past the batch)
 }
 
 template <bool SR16, typename S>
@@ -916,11 +924,10 @@ static int launch_h16(svad_engine* e, const TileArgs& a, cudaStream_t st) {
         }
         const int np = pairs[e->device & 15];
         if (np >= 1) {
-            const int bt = pick_bt(e, a.B, 2 * np);
+            const int bt = pick_bt(e, a.B);
             const int ntiles = (a.B + bt - 1) / bt;
-            int grid = ((ntiles + 1) / 2) * 2;
-            if (grid > 2 * np) grid = 2 * np;
-            const int ntiles_eff = ((ntiles + grid - 1) / grid) * grid;
+            int grid, ntiles_eff;
+            pick_grid(ntiles, 2 * np, true, &grid, &ntiles_eff);
             cfg.gridDim = dim3(grid);
             CUDA_TRY(cudaLaunchKernelEx(&cfg, kp, a, (const unsigned char*)e->d_h16_f[br], (const unsigned char*)e->d_h16_b[br], ntiles_eff, bt));
             e->launches++;
@@ -929,7 +936,8 @@ static int launch_h16(svad_engine* e, const TileArgs& a, cudaStream_t st) {
     }
     const int bt = pick_bt(e, a.B);
     const int ntiles = (a.B + bt - 1) / bt;
-    const int grid = ntiles < e->sms ? ntiles : e->sms;
+    int grid, ntiles_eff;
+    pick_grid(ntiles, e->sms, false, &grid, &ntiles_eff);
     kern<<<grid, kH16Threads, H16Map::total, st>>>(a, e->d_h16_f[br], e->d_h16_b[br], ntiles, bt);
     CUDA_TRY(cudaGetLastError());
     e->launches++;

@@ -2,6 +2,7 @@
 """Does the row stride of the audio matrix matter?  bench.py's [4096, 32768] fp32 rows are exactly 128 KB apart: the 32 streams of a
 tile read the same offset of 32 rows, i.e. addresses that differ only in bits >= 17.  Times svad_fused_h16 on the same audio with
 rows padded by `pad` samples (the C ABI takes the row stride).  Usage: h16_stride_probe.py [sr] [pads...]"""
+import os
 import sys
 from pathlib import Path
 
@@ -22,6 +23,8 @@ def main():
     m = load_silero_vad(device=0)
     m.engine.set_kernel("h16")
     m.engine.set_small_batch_max(0)
+    if os.environ.get("SVAD_TILE_ROWS"):   # streams per tile = 4 x rows (default: the batch spread over every SM)
+        m.engine.set_tile_rows(int(os.environ["SVAD_TILE_ROWS"]))
     g = torch.Generator(device="cuda").manual_seed(1)
     ref = None
     for pad in pads:
