@@ -43,7 +43,7 @@ def main():
               f"L2 -> SM bytes per launch: {num('l1tex__m_xbar2l1tex_read_bytes.sum') / 1e9:.2f} GB (the weight tapes, streamed by every CTA every chunk step)"]
     if "lts__t_sectors_srcunit_tex_op_read.sum" in m:
         lines.append(f"bytes read out of the L2 slices for the SMs: {num('lts__t_sectors_srcunit_tex_op_read.sum') * 32 / 1e9:.2f} GB "
-                     "(CTA pairs fetch half a slab each and multicast it: single-CTA launch 8.58 GB, round 1 16 GB)")
+                     "(CTA pairs fetch half a slab each and multicast it; 148 single CTAs: 8.58 GB, 148 CTAs in pairs: 6.14 GB, round 1: 16 GB)")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     tmp = Path("/tmp/_sass.csv")
     tmp.write_text(src)
