@@ -543,10 +543,13 @@ __device__ __forceinline__ void stage_reflect(const Ctx& c, int tid) {
 
 // first / last chunk of a row, or decimated input: context, zero tail and sample stride resolved per sample (cold path)
 template <bool SR16, typename S>
-__device__ __noinline__ void stage_generic(const Ctx& c, const TileArgs& a, const S* audio, int g0, int bt, long t, int warp, int lane) {
+__device__ __noinline__ void stage_generic(unsigned char* sm, const S* audio, long a_ld, long a_L, const float* a_ctx_in, long a_ctx_ld, int a_B, int a_dec,
+                                           int g0, int bt, long t, int warp, int lane) {
+    // (everything by value: a reference to the kernel's TileArgs or Ctx here would force those structs into local memory for the
+    // whole kernel, and every `a.T`, `c.bar(i)` of the hot loops would become a local load)
     using G = H16Geo<SR16>;
-    unsigned char* hi = c.sm + H16Map::R;
-    unsigned char* lo = c.sm + H16Map::R + G::XR * 64;
+    unsigned char* hi = sm + H16Map::R;
+    unsigned char* lo = sm + H16Map::R + G::XR * 64;
 #pragma unroll 1
     for (int blk = warp; blk < G::XR / 32; blk += kH16EfWarps) {
         const int m = 32 * blk + lane;
@@ -556,7 +559,7 @@ __device__ __noinline__ void stage_generic(const Ctx& c, const TileArgs& a, cons
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int sl = 16 * hf + i, g = g0 + sl;
-                w[i] = (sl < bt && g < a.B) ? kSx * window_sample<SR16, S>(audio + (long)g * a.ld, a.L, a.ctx_in ? a.ctx_in + (long)g * a.ctx_ld : nullptr, t, m, a.dec) : 0.0f;
+                w[i] = (sl < bt && g < a_B) ? kSx * window_sample<SR16, S>(audio + (long)g * a_ld, a_L, a_ctx_in ? a_ctx_in + (long)g * a_ctx_ld : nullptr, t, m, a_dec) : 0.0f;
             }
             store_row16(hi, lo, m, hf, w);
         }
@@ -686,7 +689,7 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
                         }
                     }
                 } else {
-                    stage_generic<SR16, S>(c, a, audio, g0, bt, t, w8, lane);
+                    stage_generic<SR16, S>(c.sm, audio, a.ld, a.L, a.ctx_in, a.ctx_ld, a.B, a.dec, g0, bt, t, w8, lane);
                 }
             }
             fence_async();
