@@ -605,6 +605,7 @@ __device__ __forceinline__ void run_ef(const Ctx& c, const TileArgs& a, int firs
 #define SVAD_H16_EARLY KBV
 #else
 #define SVAD_H16_EARLY 2   // 168 registers per thread: two blocks in flight across the wait, the rest loaded after it
+                           // (measured 16 kHz / 8 kHz: 1 block 2.25e8 / 2.87e8, 2 blocks 2.27e8 / 3.02e8, 3 blocks -- spills -- 2.04e8 / 2.66e8)
 #endif
 #endif
             float v[SVAD_H16_EARLY][8][4];
