@@ -917,7 +917,7 @@ static int launch_h16(svad_engine* e, const TileArgs& a, cudaStream_t st) {
             CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H16Map::total));
             cfg.gridDim = dim3(2 * (e->sms / 2));
             int n = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kp, &cfg));
+            if (cudaOccupancyMaxActiveClusters(&n, kp, &cfg) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }   // no pairs: single CTAs below
             pairs[e->device & 15] = n;
             configured_p[e->device & 15] = true;
             if (getenv("SVAD_VERBOSE")) fprintf(stderr, "svad: h16 pair mode: %d co-resident CTA pairs on %d SMs\n", n, e->sms);
@@ -929,9 +929,12 @@ static int launch_h16(svad_engine* e, const TileArgs& a, cudaStream_t st) {
             int grid, ntiles_eff;
             pick_grid(ntiles, 2 * np, true, &grid, &ntiles_eff);
             cfg.gridDim = dim3(grid);
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, kp, a, (const unsigned char*)e->d_h16_f[br], (const unsigned char*)e->d_h16_b[br], ntiles_eff, bt));
-            e->launches++;
-            return SVAD_OK;
+            if (cudaLaunchKernelEx(&cfg, kp, a, (const unsigned char*)e->d_h16_f[br], (const unsigned char*)e->d_h16_b[br], ntiles_eff, bt) == cudaSuccess) {
+                e->launches++;
+                return SVAD_OK;
+            }
+            (void)cudaGetLastError();   // the cluster launch was refused (e.g. a partitioned device): single CTAs from now on
+            e->h16_pair = 0;
         }
     }
     const int bt = pick_bt(e, a.B);
